@@ -1,0 +1,198 @@
+// c_api.cu -- extern "C" entry points declared in include/drm_b200.h.
+//
+// Plain pointers and sizes only; no torch types.  Every function validates its arguments before
+// touching the device, never throws and never synchronises (the *_host variant excepted).
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <atomic>
+#include <mutex>
+#include <string>
+#include "drm_common.cuh"
+
+namespace drm {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<int> g_fk_variant{-1};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// FK staging variant: 1 = TMA bulk copies (default), 0 = cooperative float4 copies.
+// Overridable for A/B measurements with DRMB200_FK_VARIANT or drmb200_set_option("fk_variant", v).
+int fk_variant() {
+    int v = g_fk_variant.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("DRMB200_FK_VARIANT");
+        v = e ? atoi(e) : 1;
+        g_fk_variant.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// implemented in the kernel translation units
+int fk_jacobian_device(const drmb200_topology_t*, int32_t, const float*, const float*, int64_t, float*, float*,
+                       float*, float*, cudaStream_t);
+int fk_jacobian_backward_device(const drmb200_topology_t*, int32_t, const float*, const float*, int64_t,
+                                const float*, const float*, const float*, const float*, float*, float*, void*,
+                                cudaStream_t);
+int inverse_dynamics_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*,
+                            int64_t, uint32_t, float*, cudaStream_t);
+int inverse_dynamics_backward_device(const drmb200_topology_t*, const float*, const float*, const float*,
+                                     const float*, int64_t, uint32_t, const float*, float*, float*, float*,
+                                     float*, void*, cudaStream_t);
+int64_t table_grad_workspace_bytes(const drmb200_topology_t*, int64_t);
+
+// ---------------------------------------------------------------------------------------------
+// host-buffer pipeline for FK + Jacobian
+// ---------------------------------------------------------------------------------------------
+struct HostPipe {
+    int device = -1;
+    static constexpr int NSTAGE = 3;
+    int64_t chunk = 0;          // configurations per stage buffer
+    int n_dofs = 0;
+    cudaStream_t stream[NSTAGE] = {};
+    float* d_q[NSTAGE] = {};
+    float* d_pos[NSTAGE] = {};
+    float* d_quat[NSTAGE] = {};
+    float* d_jl[NSTAGE] = {};
+    float* d_ja[NSTAGE] = {};
+    void release() {
+        for (int s = 0; s < NSTAGE; ++s) {
+            if (d_q[s]) cudaFree(d_q[s]);
+            if (d_pos[s]) cudaFree(d_pos[s]);
+            if (d_quat[s]) cudaFree(d_quat[s]);
+            if (d_jl[s]) cudaFree(d_jl[s]);
+            if (d_ja[s]) cudaFree(d_ja[s]);
+            if (stream[s]) cudaStreamDestroy(stream[s]);
+            d_q[s] = d_pos[s] = d_quat[s] = d_jl[s] = d_ja[s] = nullptr;
+            stream[s] = nullptr;
+        }
+        chunk = 0;
+    }
+};
+static HostPipe g_pipe;
+static std::mutex g_pipe_mu;
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            set_error("%s: %s", #call, cudaGetErrorString(e__));                              \
+            return DRMB200_ECUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+static int fk_jacobian_host_impl(const drmb200_topology_t* topo, int32_t ee_link, int32_t device,
+                                 const float* table, const float* q_host, int64_t batch, float* pos_host,
+                                 float* quat_host, float* jl_host, float* ja_host) {
+    if (topo == nullptr || q_host == nullptr || table == nullptr) { set_error("null argument"); return DRMB200_EINVAL; }
+    if (batch < 0) { set_error("batch < 0"); return DRMB200_EINVAL; }
+    if ((jl_host == nullptr) != (ja_host == nullptr)) { set_error("jac_lin/jac_ang must both be given or both null"); return DRMB200_EINVAL; }
+    if (batch == 0) return DRMB200_OK;
+    const int n = topo->n_dofs;
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    CK(cudaSetDevice(device));
+    // 64 Ki configurations per chunk: 14.7 MB per stage for a 7-DoF arm, large enough for PCIe
+    // efficiency, small enough that three stages overlap H2D / compute / D2H.
+    const int64_t want_chunk = 65536;
+    if (g_pipe.device != device || g_pipe.n_dofs != n || g_pipe.chunk != want_chunk) {
+        g_pipe.release();
+        g_pipe.device = device;
+        g_pipe.n_dofs = n;
+        for (int s = 0; s < HostPipe::NSTAGE; ++s) {
+            CK(cudaStreamCreateWithFlags(&g_pipe.stream[s], cudaStreamNonBlocking));
+            CK(cudaMalloc(&g_pipe.d_q[s], want_chunk * n * sizeof(float)));
+            CK(cudaMalloc(&g_pipe.d_pos[s], want_chunk * 3 * sizeof(float)));
+            CK(cudaMalloc(&g_pipe.d_quat[s], want_chunk * 4 * sizeof(float)));
+            CK(cudaMalloc(&g_pipe.d_jl[s], want_chunk * 3 * n * sizeof(float)));
+            CK(cudaMalloc(&g_pipe.d_ja[s], want_chunk * 3 * n * sizeof(float)));
+        }
+        g_pipe.chunk = want_chunk;
+    }
+    int64_t done = 0;
+    int s = 0;
+    while (done < batch) {
+        const int64_t b = (batch - done < g_pipe.chunk) ? (batch - done) : g_pipe.chunk;
+        cudaStream_t st = g_pipe.stream[s];
+        // stream order on `st` guarantees the previous D2H out of this stage's buffers has finished
+        CK(cudaMemcpyAsync(g_pipe.d_q[s], q_host + done * n, b * n * sizeof(float), cudaMemcpyHostToDevice, st));
+        int rc = fk_jacobian_device(topo, ee_link, table, g_pipe.d_q[s], b, pos_host ? g_pipe.d_pos[s] : nullptr,
+                                    quat_host ? g_pipe.d_quat[s] : nullptr, jl_host ? g_pipe.d_jl[s] : nullptr,
+                                    ja_host ? g_pipe.d_ja[s] : nullptr, st);
+        if (rc != DRMB200_OK) return rc;
+        if (pos_host) CK(cudaMemcpyAsync(pos_host + done * 3, g_pipe.d_pos[s], b * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (quat_host) CK(cudaMemcpyAsync(quat_host + done * 4, g_pipe.d_quat[s], b * 4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (jl_host) {
+            CK(cudaMemcpyAsync(jl_host + done * 3 * n, g_pipe.d_jl[s], b * 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ja_host + done * 3 * n, g_pipe.d_ja[s], b * 3 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        done += b;
+        s = (s + 1) % HostPipe::NSTAGE;
+    }
+    for (int i = 0; i < HostPipe::NSTAGE; ++i) CK(cudaStreamSynchronize(g_pipe.stream[i]));
+    return DRMB200_OK;
+}
+
+}  // namespace drm
+
+extern "C" {
+
+int drmb200_version(void) { return 100; }   // 0.1.0
+const char* drmb200_last_error(void) { return drm::g_err; }
+int64_t drmb200_launch_count(void) { return drm::g_launches.load(); }
+
+// not part of the reference-facing surface: A/B switch used by bench.py and the tests
+int drmb200_set_option(const char* name, int value) {
+    if (name != nullptr && std::string(name) == "fk_variant") { drm::g_fk_variant.store(value); return DRMB200_OK; }
+    drm::set_error("unknown option");
+    return DRMB200_EINVAL;
+}
+
+int drmb200_fk_jacobian(const drmb200_topology_t* topo, int32_t ee_link, const float* table, const float* q,
+                        int64_t batch, float* pos, float* quat, float* jac_lin, float* jac_ang, void* cuda_stream) {
+    return drm::fk_jacobian_device(topo, ee_link, table, q, batch, pos, quat, jac_lin, jac_ang,
+                                   static_cast<cudaStream_t>(cuda_stream));
+}
+
+int64_t drmb200_table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch) {
+    return drm::table_grad_workspace_bytes(topo, batch);
+}
+
+int drmb200_fk_jacobian_backward(const drmb200_topology_t* topo, int32_t ee_link, const float* table, const float* q,
+                                 int64_t batch, const float* g_pos, const float* g_quat, const float* g_jac_lin,
+                                 const float* g_jac_ang, float* q_grad, float* table_grad, void* workspace,
+                                 void* cuda_stream) {
+    return drm::fk_jacobian_backward_device(topo, ee_link, table, q, batch, g_pos, g_quat, g_jac_lin, g_jac_ang,
+                                            q_grad, table_grad, workspace, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_inverse_dynamics(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                             const float* qdd, int64_t batch, uint32_t flags, float* tau, void* cuda_stream) {
+    return drm::inverse_dynamics_device(topo, table, q, qd, qdd, batch, flags, tau,
+                                        static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo, const float* table, const float* q,
+                                      const float* qd, const float* qdd, int64_t batch, uint32_t flags,
+                                      const float* g_tau, float* q_grad, float* qd_grad, float* qdd_grad,
+                                      float* table_grad, void* workspace, void* cuda_stream) {
+    return drm::inverse_dynamics_backward_device(topo, table, q, qd, qdd, batch, flags, g_tau, q_grad, qd_grad,
+                                                 qdd_grad, table_grad, workspace,
+                                                 static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_fk_jacobian_host(const drmb200_topology_t* topo, int32_t ee_link, int32_t device, const float* table,
+                             const float* q_host, int64_t batch, float* pos_host, float* quat_host,
+                             float* jac_lin_host, float* jac_ang_host) {
+    return drm::fk_jacobian_host_impl(topo, ee_link, device, table, q_host, batch, pos_host, quat_host, jac_lin_host,
+                                      jac_ang_host);
+}
+
+}  // extern "C"

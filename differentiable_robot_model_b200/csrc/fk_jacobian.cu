@@ -1,0 +1,292 @@
+// fk_jacobian.cu -- batched forward kinematics + geometric end-effector Jacobian (sm_100a).
+//
+// Replaces, in ONE launch, the reference's per-link PyTorch graph for
+//   DifferentiableRobotModel.compute_forward_kinematics   (robot_model.py:224-248)
+//   DifferentiableRobotModel.compute_endeffector_jacobian (robot_model.py:627-667)
+// i.e. update_joint_state (rigid_body.py:130-157), the chain walk of update_kinematic_state
+// (robot_model.py:173-193), CoordinateTransform.get_quaternion (spatial_vector_algebra.py:108-136)
+// and the ee->root Jacobian walk (robot_model.py:652-665).
+//
+// Mapping: one thread per joint configuration, TILE configurations per CTA.
+//   * The outputs of a link depend only on its ancestors, so the kernel walks just the root->ee
+//     chain (the "path program", a by-value kernel parameter living in the constant bank).
+//   * q tile in / (pos, quat, J_lin, J_ang) tiles out are staged through shared memory in the
+//     SAME row-major layout as global memory, so each tile moves as one contiguous block:
+//       variant 1: TMA 1-D bulk copies (cp.async.bulk, mbarrier completion) issued by one thread;
+//       variant 0: cooperative float4 copies (also the fallback for ragged tails / unaligned bases).
+//     Per-thread smem rows have odd strides for odd n_dofs (7 -> 7, 21 floats), hence no bank conflicts.
+//   * The world rotation R (9) and position p (3) stay in registers along the chain.  Jacobian
+//     columns need p_ee, known only at the end of the walk, so during the walk each path joint
+//     stores z_i (= its J_ang column, final) and z_i x p_i in the J_lin slot of the smem tile; a
+//     short second pass rewrites J_lin = z_i x p_ee - z_i x p_i.
+//   * The float link table (F, r per link; differentiable, device memory) is staged once per CTA
+//     into shared memory and read with warp-broadcast LDS.128.
+//
+// Algorithmic HBM bytes per configuration: 4n (q) + 12 (pos) + 16 (quat) + 24n (J) = 28n + 28
+// (224 B for the 7-DoF Kuka iiwa) -- SURVEY.md section 8(d).
+#include "drm_common.cuh"
+
+namespace drm {
+
+constexpr int FK_TILE = 256;       // configurations per CTA == threads per CTA
+
+struct FkArgs {
+    const float* __restrict__ table;     // [n_links, 28]
+    const float* __restrict__ q;         // [B, n]
+    float* __restrict__ pos;             // [B, 3] or null
+    float* __restrict__ quat;            // [B, 4] or null
+    float* __restrict__ jlin;            // [B, 3, n] or null
+    float* __restrict__ jang;            // [B, 3, n] or null
+    int64_t batch;
+    int32_t bulk_ok;                     // all base pointers 16-byte aligned
+};
+
+// shared-memory carve-up (floats), natural global layout per region
+struct FkSmemLayout {
+    int q, pos, quat, jlin, jang, table, total_floats;
+    __host__ __device__ FkSmemLayout(int n, int path_len, bool with_jac) {
+        int o = 0;
+        quat = o; o += FK_TILE * 4;            // 16-byte aligned rows first
+        q = o;    o += FK_TILE * n;
+        pos = o;  o += FK_TILE * 3;
+        jlin = o; o += with_jac ? FK_TILE * 3 * n : 0;
+        jang = o; o += with_jac ? FK_TILE * 3 * n : 0;
+        table = o; o += path_len * 12;
+        total_floats = o;
+    }
+};
+
+// cooperative linear copy global -> shared / shared -> global (layout identical on both sides)
+__device__ __forceinline__ void coop_copy_in(float* s, const float* g, int nfloats, bool vec_ok) {
+    if (vec_ok && (nfloats & 3) == 0) {
+        const float4* g4 = reinterpret_cast<const float4*>(g);
+        float4* s4 = reinterpret_cast<float4*>(s);
+        for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) s4[i] = __ldg(g4 + i);
+    } else {
+        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) s[i] = __ldg(g + i);
+    }
+}
+__device__ __forceinline__ void coop_copy_out(float* g, const float* s, int nfloats, bool vec_ok) {
+    if (vec_ok && (nfloats & 3) == 0) {
+        float4* g4 = reinterpret_cast<float4*>(g);
+        const float4* s4 = reinterpret_cast<const float4*>(s);
+        for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) g4[i] = s4[i];
+    } else {
+        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) g[i] = s[i];
+    }
+}
+
+template <bool WITH_JAC, bool USE_BULK>
+__global__ void __launch_bounds__(FK_TILE, 3)
+fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int n = prog.n_dofs;
+    const FkSmemLayout L(n, prog.len, WITH_JAC);
+    float* s_q = smem + L.q;
+    float* s_pos = smem + L.pos;
+    float* s_quat = smem + L.quat;
+    float* s_jlin = smem + L.jlin;
+    float* s_jang = smem + L.jang;
+    float* s_tab = smem + L.table;
+
+    const int tid = threadIdx.x;
+    const int64_t tile_start = (int64_t)blockIdx.x * FK_TILE;
+    const int valid = (int)min((int64_t)FK_TILE, args.batch - tile_start);
+    // bulk copies need 16-byte multiples: rows are 4n / 12 / 16 / 12n bytes -> valid % 4 == 0
+    const bool bulk = USE_BULK && args.bulk_ok && ((valid & 3) == 0);
+    const bool vec_ok = args.bulk_ok;   // base pointers 16-byte aligned; tile offsets always are
+
+    // ---- stage inputs --------------------------------------------------------------------------
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&mbar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = (uint32_t)valid * n * 4u;
+            mbar_arrive_expect_tx(&mbar, bytes);
+            bulk_g2s(s_q, args.q + tile_start * n, bytes, &mbar);
+        }
+    } else {
+        coop_copy_in(s_q, args.q + tile_start * n, valid * n, vec_ok);
+    }
+    // link-table rows of the path (F, r) -> smem
+    for (int i = tid; i < prog.len * 12; i += FK_TILE) {
+        int k = i / 12, e = i - k * 12;
+        s_tab[i] = __ldg(args.table + (int)prog.link[k] * DRMB200_TABLE_STRIDE + e);
+    }
+    if (WITH_JAC && !prog.full_cover) {      // columns of joints off the path stay zero
+        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* j4 = reinterpret_cast<float4*>(s_jlin);      // jlin and jang are adjacent
+        for (int i = tid; i < (FK_TILE * 6 * n) / 4; i += FK_TILE) j4[i] = z4;
+    }
+    __syncthreads();
+    if (bulk) mbar_wait(&mbar, 0);
+
+    // ---- chain walk ----------------------------------------------------------------------------
+    if (tid < valid) {
+        M3 R = identity3();
+        V3 p = v3(0.f, 0.f, 0.f);
+        const float* qrow = s_q + tid * n;
+        float* jl = s_jlin + tid * 3 * n;
+        float* ja = s_jang + tid * 3 * n;
+
+        for (int k = 0; k < prog.len; ++k) {
+            const float4* t4 = reinterpret_cast<const float4*>(s_tab + k * 12);
+            const float4 f0 = t4[0], f1 = t4[1], f2 = t4[2];
+            M3 F; F.a00 = f0.x; F.a01 = f0.y; F.a02 = f0.z; F.a10 = f0.w; F.a11 = f1.x; F.a12 = f1.y;
+            F.a20 = f1.z; F.a21 = f1.w; F.a22 = f2.x;
+            const V3 r = v3(f2.y, f2.z, f2.w);
+
+            p = mul_add(R, r, p);            // p_i = R_parent r_i + p_parent
+            R = mul(R, F);                   // R_parent F_i
+            const int ax = prog.axis[k];
+            if (ax != 0) {
+                const int a = (ax > 0 ? ax : -ax) - 1;
+                float th = qrow[prog.dof[k]];
+                if (ax < 0) th = -th;        // angle = sign(axis) * q   (rigid_body.py:149-154)
+                float sn, cs;
+                sincos_pi2(th, sn, cs);
+                if (WITH_JAC) {
+                    // z_i = R_i s_i: the joint rotation leaves its own axis column unchanged
+                    V3 z = col(R, a);
+                    if (ax < 0) z = v3(-z.x, -z.y, -z.z);
+                    const V3 m = cross(z, p);
+                    const int c = prog.dof[k];
+                    ja[c] = z.x; ja[n + c] = z.y; ja[2 * n + c] = z.z;
+                    jl[c] = m.x; jl[n + c] = m.y; jl[2 * n + c] = m.z;
+                }
+                apply_joint_rotation(R, a, cs, sn);
+            }
+        }
+
+        if (args.pos != nullptr) { s_pos[tid * 3 + 0] = p.x; s_pos[tid * 3 + 1] = p.y; s_pos[tid * 3 + 2] = p.z; }
+        if (args.quat != nullptr) reinterpret_cast<float4*>(s_quat)[tid] = quat_xyzw(R);
+
+        if (WITH_JAC) {
+            // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
+            for (int k = 0; k < prog.len; ++k) {
+                if (prog.axis[k] == 0) continue;
+                const int c = prog.dof[k];
+                const V3 z = v3(ja[c], ja[n + c], ja[2 * n + c]);
+                const V3 m = v3(jl[c], jl[n + c], jl[2 * n + c]);
+                const V3 j = cross_add(z, p, v3(-m.x, -m.y, -m.z));
+                jl[c] = j.x; jl[n + c] = j.y; jl[2 * n + c] = j.z;
+            }
+        }
+    }
+
+    // ---- stream the output tiles back ----------------------------------------------------------
+    if (bulk) {
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the async proxy
+        __syncthreads();
+        if (tid == 0) {
+            if (args.pos != nullptr) bulk_s2g(args.pos + tile_start * 3, s_pos, (uint32_t)valid * 12u);
+            if (args.quat != nullptr) bulk_s2g(args.quat + tile_start * 4, s_quat, (uint32_t)valid * 16u);
+            if (WITH_JAC) {
+                bulk_s2g(args.jlin + tile_start * 3 * n, s_jlin, (uint32_t)valid * 12u * n);
+                bulk_s2g(args.jang + tile_start * 3 * n, s_jang, (uint32_t)valid * 12u * n);
+            }
+            bulk_commit();
+            bulk_wait_read<0>();             // smem must stay intact until the copy engine has read it
+        }
+    } else {
+        __syncthreads();
+        if (args.pos != nullptr) coop_copy_out(args.pos + tile_start * 3, s_pos, valid * 3, vec_ok);
+        if (args.quat != nullptr) coop_copy_out(args.quat + tile_start * 4, s_quat, valid * 4, vec_ok);
+        if (WITH_JAC) {
+            coop_copy_out(args.jlin + tile_start * 3 * n, s_jlin, valid * 3 * n, vec_ok);
+            coop_copy_out(args.jang + tile_start * 3 * n, s_jang, valid * 3 * n, vec_ok);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int build_path_program(const drmb200_topology_t* topo, int32_t ee_link, PathProgram* prog) {
+    if (topo == nullptr) { set_error("topology is null"); return DRMB200_EINVAL; }
+    if (topo->n_links < 1 || topo->n_links > DRMB200_MAX_LINKS) {
+        set_error("n_links=%d outside [1, %d]", topo->n_links, DRMB200_MAX_LINKS);
+        return DRMB200_ELIMIT;
+    }
+    if (ee_link < 0 || ee_link >= topo->n_links) {
+        set_error("ee_link=%d outside [0, %d)", ee_link, topo->n_links);
+        return DRMB200_EINVAL;
+    }
+    int chain[DRMB200_MAX_LINKS];
+    int len = 0;
+    for (int l = ee_link; l > 0; l = topo->parent[l]) {
+        if (topo->parent[l] < 0 || topo->parent[l] >= l) {
+            set_error("link %d: parent %d violates topological order", l, (int)topo->parent[l]);
+            return DRMB200_EINVAL;
+        }
+        chain[len++] = l;
+    }
+    prog->len = len;
+    prog->n_dofs = topo->n_dofs;
+    int covered = 0;
+    for (int k = 0; k < len; ++k) {
+        int l = chain[len - 1 - k];
+        prog->link[k] = (int8_t)l;
+        prog->axis[k] = topo->axis[l];
+        prog->dof[k] = topo->dof[l];
+        if (topo->axis[l] != 0) {
+            if (topo->dof[l] < 0 || topo->dof[l] >= topo->n_dofs || abs((int)topo->axis[l]) > 3) {
+                set_error("link %d: bad dof/axis (%d, %d)", l, (int)topo->dof[l], (int)topo->axis[l]);
+                return DRMB200_EINVAL;
+            }
+            ++covered;
+        }
+    }
+    prog->full_cover = (covered == topo->n_dofs) ? 1 : 0;
+    return DRMB200_OK;
+}
+
+template <bool WITH_JAC, bool USE_BULK>
+static int launch_fk(const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
+    const FkSmemLayout L(prog.n_dofs, prog.len, WITH_JAC);
+    const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
+    auto kern = fk_jacobian_kernel<WITH_JAC, USE_BULK>;
+    static size_t configured_by_dev[64] = {0};     // per instantiation, per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_by_dev[dev & 63];
+    if (smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
+        configured = smem_bytes;
+    }
+    const int64_t tiles = (args.batch + FK_TILE - 1) / FK_TILE;
+    kern<<<(unsigned)tiles, FK_TILE, smem_bytes, stream>>>(prog, args);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("fk_jacobian launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
+    count_launch();
+    return DRMB200_OK;
+}
+
+int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const float* table, const float* q,
+                       int64_t batch, float* pos, float* quat, float* jlin, float* jang, cudaStream_t stream) {
+    PathProgram prog;
+    int rc = build_path_program(topo, ee_link, &prog);
+    if (rc != DRMB200_OK) return rc;
+    if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
+    if ((jlin == nullptr) != (jang == nullptr)) { set_error("jac_lin and jac_ang must both be given or both be null"); return DRMB200_EINVAL; }
+    if (batch == 0) return DRMB200_OK;
+    if (table == nullptr || q == nullptr) { set_error("table / q is null"); return DRMB200_EINVAL; }
+    if (pos == nullptr && quat == nullptr && jlin == nullptr) return DRMB200_OK;
+    if ((batch + FK_TILE - 1) / FK_TILE > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
+
+    FkArgs args;
+    args.table = table; args.q = q; args.pos = pos; args.quat = quat; args.jlin = jlin; args.jang = jang;
+    args.batch = batch;
+    auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    args.bulk_ok = (al16(q) && al16(pos) && al16(quat) && al16(jlin) && al16(jang)) ? 1 : 0;
+
+    const bool with_jac = jlin != nullptr;
+    const bool use_bulk = fk_variant() != 0;
+    if (with_jac) return use_bulk ? launch_fk<true, true>(prog, args, stream) : launch_fk<true, false>(prog, args, stream);
+    return use_bulk ? launch_fk<false, true>(prog, args, stream) : launch_fk<false, false>(prog, args, stream);
+}
+
+}  // namespace drm

@@ -1,0 +1,325 @@
+// rnea.cu -- batched recursive Newton-Euler inverse dynamics (sm_100a).
+//
+// Replaces, in ONE launch, DifferentiableRobotModel.compute_inverse_dynamics (robot_model.py:306-375):
+// update_kinematic_state (robot_model.py:140-195, velocities), update_joint_acc (rigid_body.py:159-165),
+// iterative_newton_euler (robot_model.py:251-303: acceleration pass root->leaves, force pass
+// leaves->root, spatial_vector_algebra.py:204-236, 281-291, 321-338), the axis projection
+// (robot_model.py:353-365) and the damping term (robot_model.py:368-373).
+//
+// Closed form (verified against the reference), link i, parent p,
+// M = F_i Q_i(q), r = trans_i, s = signed joint axis, wJ = s qd:
+//   w_i  = M^T w_p + wJ                 v_i = M^T (v_p - r x w_p)
+//   al_i = M^T al_p + s qdd + w_i x wJ  a_i = M^T (a_p - r x al_p) + v_i x wJ      (a_0 = (0,0,9.81))
+//   h(W,V) = ( m V - mc x W ,  I_o W + mc x V )
+//   f_i  = h_lin(al,a) + w x h_lin(w,v)
+//   n_i  = h_ang(al,a) + w x h_ang(w,v) + v x h_lin(w,v)
+//   f_p += M f_i ;  n_p += r x (M f_i) + M n_i ;  tau_k = s . n_i + d_i qd_k
+//
+// Mapping: one thread per configuration (RNEA_TILE per CTA).  The motion state (w, v, al, a) of the
+// current link lives in registers; only branch points of the tree spill it to shared-memory slots
+// (host-computed "tree program", by-value kernel parameter).  Per-link body wrenches (f, n) and the
+// joint (cos, sin) are kept in shared memory, slot-major ([slot][thread] -> conflict-free), for the
+// leaves->root pass, where children accumulate into their parent's slot.
+// q / qd / qdd tiles in and the tau tile out are staged in the global row-major layout and moved
+// with TMA 1-D bulk copies (cooperative float4 copies for ragged tails / unaligned bases).
+//
+// Algorithmic HBM bytes per configuration: 12n in + 4n out = 16n (112 B at n = 7).  At roughly
+// 2 kflop per 7-DoF configuration the kernel is FP32-issue-bound, not HBM-bound.
+#include "drm_common.cuh"
+
+namespace drm {
+
+constexpr int RNEA_TILE = 128;
+constexpr float GRAVITY = 9.81f;     // robot_model.py:347
+
+struct RneaArgs {
+    const float* __restrict__ table;
+    const float* __restrict__ q;
+    const float* __restrict__ qd;
+    const float* __restrict__ qdd;
+    float* __restrict__ tau;
+    int64_t batch;
+    uint32_t flags;
+    int32_t bulk_ok;
+};
+
+struct RneaSmemLayout {
+    int q, qd, qdd, tau, table, link, slots, total_floats;
+    __host__ __device__ RneaSmemLayout(int n, int n_links, int n_slots) {
+        int o = 0;
+        q = o;   o += RNEA_TILE * n;
+        qd = o;  o += RNEA_TILE * n;
+        qdd = o; o += RNEA_TILE * n;
+        tau = o; o += RNEA_TILE * n;
+        table = o; o += n_links * DRMB200_TABLE_STRIDE;
+        link = o;  o += n_links * 8 * RNEA_TILE;          // per link: f(3) n(3) cos sin, slot-major
+        slots = o; o += n_slots * 12 * RNEA_TILE;         // branch-point motion states
+        total_floats = o;
+    }
+};
+
+struct LinkConsts {   // one table row, read by warp-broadcast LDS.128
+    M3 F; V3 r; M3 Io; V3 mc; float m, d;
+};
+__device__ __forceinline__ LinkConsts load_link(const float* row) {
+    const float4* t = reinterpret_cast<const float4*>(row);
+    const float4 a = t[0], b = t[1], c = t[2], d = t[3], e = t[4], f = t[5], g = t[6];
+    LinkConsts L;
+    L.F.a00 = a.x; L.F.a01 = a.y; L.F.a02 = a.z; L.F.a10 = a.w; L.F.a11 = b.x; L.F.a12 = b.y;
+    L.F.a20 = b.z; L.F.a21 = b.w; L.F.a22 = c.x;
+    L.r = v3(c.y, c.z, c.w);
+    L.Io.a00 = d.x; L.Io.a01 = d.y; L.Io.a02 = d.z; L.Io.a10 = d.w; L.Io.a11 = e.x; L.Io.a12 = e.y;
+    L.Io.a20 = e.z; L.Io.a21 = e.w; L.Io.a22 = f.x;
+    L.mc = v3(f.y, f.z, f.w);
+    L.m = g.x; L.d = g.y;
+    return L;
+}
+__device__ __forceinline__ V3 axis_vec(int a, float w) {    // w * e_a, a uniform
+    return v3(a == 0 ? w : 0.f, a == 1 ? w : 0.f, a == 2 ? w : 0.f);
+}
+__device__ __forceinline__ float comp(V3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+
+__device__ __forceinline__ void coop_copy(float* dst, const float* src, int nfloats, bool vec_ok) {
+    if (vec_ok && (nfloats & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) d4[i] = s4[i];
+    } else {
+        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+__global__ void __launch_bounds__(RNEA_TILE, 4)
+rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
+    extern __shared__ __align__(128) float smem[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int n = prog.n_dofs;
+    const int N = prog.n_links;
+    const RneaSmemLayout L(n, N, prog.n_slots);
+    float* s_q = smem + L.q;
+    float* s_qd = smem + L.qd;
+    float* s_qdd = smem + L.qdd;
+    float* s_tau = smem + L.tau;
+    float* s_tab = smem + L.table;
+    float* s_link = smem + L.link;
+    float* s_slot = smem + L.slots;
+
+    const int tid = threadIdx.x;
+    const int64_t tile_start = (int64_t)blockIdx.x * RNEA_TILE;
+    const int valid = (int)min((int64_t)RNEA_TILE, args.batch - tile_start);
+    const bool vec_ok = args.bulk_ok;
+    const bool bulk = args.bulk_ok && ((valid & 3) == 0);
+
+    if (bulk) {
+        if (tid == 0) {
+            mbar_init(&mbar, 1);
+            fence_mbar_init();
+            const uint32_t bytes = (uint32_t)valid * n * 4u;
+            mbar_arrive_expect_tx(&mbar, 3u * bytes);
+            bulk_g2s(s_q, args.q + tile_start * n, bytes, &mbar);
+            bulk_g2s(s_qd, args.qd + tile_start * n, bytes, &mbar);
+            bulk_g2s(s_qdd, args.qdd + tile_start * n, bytes, &mbar);
+        }
+    } else {
+        coop_copy(s_q, args.q + tile_start * n, valid * n, vec_ok);
+        coop_copy(s_qd, args.qd + tile_start * n, valid * n, vec_ok);
+        coop_copy(s_qdd, args.qdd + tile_start * n, valid * n, vec_ok);
+    }
+    for (int i = tid; i < N * DRMB200_TABLE_STRIDE; i += RNEA_TILE) s_tab[i] = __ldg(args.table + i);
+    __syncthreads();
+    if (bulk) mbar_wait(&mbar, 0);
+
+    if (tid < valid) {
+        const float* qrow = s_q + tid * n;
+        const float* qdrow = s_qd + tid * n;
+        const float* qddrow = s_qdd + tid * n;
+        float* taurow = s_tau + tid * n;
+        const float g = (args.flags & DRMB200_GRAVITY) ? GRAVITY : 0.f;
+        const bool damp = (args.flags & DRMB200_DAMPING) != 0;
+
+        // ---- pass 1: root -> leaves, motion state + body wrench ------------------------------------
+        V3 w = v3(0.f, 0.f, 0.f), v = w, al = w, a = w;     // state of the previously processed link
+        for (int i = 1; i < N; ++i) {
+            const LinkConsts C = load_link(s_tab + i * DRMB200_TABLE_STRIDE);
+            const int src = prog.psrc[i];
+            V3 wp, vp, alp, ap;
+            if (src == 0) { wp = w; vp = v; alp = al; ap = a; }
+            else if (src < 0) { wp = vp = alp = v3(0.f, 0.f, 0.f); ap = v3(0.f, 0.f, g); }
+            else {
+                const float* sl = s_slot + (src - 1) * 12 * RNEA_TILE + tid;
+                wp = v3(sl[0], sl[RNEA_TILE], sl[2 * RNEA_TILE]);
+                vp = v3(sl[3 * RNEA_TILE], sl[4 * RNEA_TILE], sl[5 * RNEA_TILE]);
+                alp = v3(sl[6 * RNEA_TILE], sl[7 * RNEA_TILE], sl[8 * RNEA_TILE]);
+                ap = v3(sl[9 * RNEA_TILE], sl[10 * RNEA_TILE], sl[11 * RNEA_TILE]);
+            }
+            M3 M = C.F;
+            const int ax = prog.axis[i];
+            float cs = 1.f, sn = 0.f;
+            int ai = 0;
+            float qd_s = 0.f, qdd_s = 0.f;           // signed joint rate / acceleration along +e_ai
+            if (ax != 0) {
+                ai = (ax > 0 ? ax : -ax) - 1;
+                const int c = prog.dof[i];
+                float th = qrow[c];
+                qd_s = qdrow[c];
+                qdd_s = qddrow[c];
+                if (ax < 0) { th = -th; qd_s = -qd_s; qdd_s = -qdd_s; }
+                sincos_pi2(th, sn, cs);
+                apply_joint_rotation(M, ai, cs, sn);
+            }
+            const V3 wJ = axis_vec(ai, qd_s);
+            // velocities (robot_model.py:183-193)
+            w = mulT(M, wp) + wJ;
+            v = mulT(M, cross_add(wp, C.r, vp));                 // v_p - r x w_p = v_p + w_p x r
+            // accelerations (robot_model.py:269-277)
+            al = mulT(M, alp) + axis_vec(ai, qdd_s) + cross(w, wJ);
+            a = mulT(M, cross_add(alp, C.r, ap)) + cross(v, wJ);
+            // body wrench (robot_model.py:289-293; spatial_vector_algebra.py:321-338)
+            const V3 hl_a = C.m * a - cross(C.mc, al);
+            const V3 ha_a = mul_add(C.Io, al, cross(C.mc, a));
+            const V3 hl_v = C.m * v - cross(C.mc, w);
+            const V3 ha_v = mul_add(C.Io, w, cross(C.mc, v));
+            const V3 f = cross_add(w, hl_v, hl_a);
+            const V3 nn = cross_add(w, ha_v, cross_add(v, hl_v, ha_a));
+            float* lk = s_link + i * 8 * RNEA_TILE + tid;
+            lk[0] = f.x; lk[RNEA_TILE] = f.y; lk[2 * RNEA_TILE] = f.z;
+            lk[3 * RNEA_TILE] = nn.x; lk[4 * RNEA_TILE] = nn.y; lk[5 * RNEA_TILE] = nn.z;
+            lk[6 * RNEA_TILE] = cs; lk[7 * RNEA_TILE] = sn;
+            const int sv = prog.save[i];
+            if (sv >= 0) {
+                float* sl = s_slot + sv * 12 * RNEA_TILE + tid;
+                sl[0] = w.x; sl[RNEA_TILE] = w.y; sl[2 * RNEA_TILE] = w.z;
+                sl[3 * RNEA_TILE] = v.x; sl[4 * RNEA_TILE] = v.y; sl[5 * RNEA_TILE] = v.z;
+                sl[6 * RNEA_TILE] = al.x; sl[7 * RNEA_TILE] = al.y; sl[8 * RNEA_TILE] = al.z;
+                sl[9 * RNEA_TILE] = a.x; sl[10 * RNEA_TILE] = a.y; sl[11 * RNEA_TILE] = a.z;
+            }
+        }
+
+        // ---- pass 2: leaves -> root, wrench propagation + joint torques (robot_model.py:284-301, 353-373)
+        for (int i = N - 1; i >= 1; --i) {
+            const float* lk = s_link + i * 8 * RNEA_TILE + tid;
+            const V3 f = v3(lk[0], lk[RNEA_TILE], lk[2 * RNEA_TILE]);
+            const V3 nn = v3(lk[3 * RNEA_TILE], lk[4 * RNEA_TILE], lk[5 * RNEA_TILE]);
+            const int ax = prog.axis[i];
+            if (ax != 0) {
+                const int ai = (ax > 0 ? ax : -ax) - 1;
+                const int c = prog.dof[i];
+                float t = comp(nn, ai);
+                if (ax < 0) t = -t;
+                if (damp) t = fmaf(s_tab[i * DRMB200_TABLE_STRIDE + 25], qdrow[c], t);
+                taurow[c] = t;
+            }
+            const int p = prog.parent[i];
+            if (p > 0) {
+                const float4* t4 = reinterpret_cast<const float4*>(s_tab + i * DRMB200_TABLE_STRIDE);
+                const float4 f0 = t4[0], f1 = t4[1], f2 = t4[2];
+                M3 M; M.a00 = f0.x; M.a01 = f0.y; M.a02 = f0.z; M.a10 = f0.w; M.a11 = f1.x; M.a12 = f1.y;
+                M.a20 = f1.z; M.a21 = f1.w; M.a22 = f2.x;
+                const V3 r = v3(f2.y, f2.z, f2.w);
+                if (ax != 0) apply_joint_rotation(M, (ax > 0 ? ax : -ax) - 1, lk[6 * RNEA_TILE], lk[7 * RNEA_TILE]);
+                const V3 fp = mul(M, f);                           // SpatialForceVec.transform (sva:281-291)
+                const V3 np = cross_add(r, fp, mul(M, nn));
+                float* pk = s_link + p * 8 * RNEA_TILE + tid;
+                pk[0] += fp.x; pk[RNEA_TILE] += fp.y; pk[2 * RNEA_TILE] += fp.z;
+                pk[3 * RNEA_TILE] += np.x; pk[4 * RNEA_TILE] += np.y; pk[5 * RNEA_TILE] += np.z;
+            }
+        }
+    }
+
+    if (bulk) {
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            bulk_s2g(args.tau + tile_start * n, s_tau, (uint32_t)valid * n * 4u);
+            bulk_commit();
+            bulk_wait_read<0>();
+        }
+    } else {
+        __syncthreads();
+        coop_copy(args.tau + tile_start * n, s_tau, valid * n, vec_ok);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int build_tree_program(const drmb200_topology_t* topo, TreeProgram* prog) {
+    if (topo == nullptr) { set_error("topology is null"); return DRMB200_EINVAL; }
+    const int N = topo->n_links;
+    if (N < 1 || N > DRMB200_MAX_LINKS) { set_error("n_links=%d outside [1, %d]", N, DRMB200_MAX_LINKS); return DRMB200_ELIMIT; }
+    if (topo->n_dofs < 0 || topo->n_dofs > N) { set_error("n_dofs=%d inconsistent with n_links=%d", topo->n_dofs, N); return DRMB200_EINVAL; }
+    prog->n_links = N;
+    prog->n_dofs = topo->n_dofs;
+    int last_far_child[DRMB200_MAX_LINKS];      // last child c of i with c != i+1, or -1
+    for (int i = 0; i < N; ++i) last_far_child[i] = -1;
+    for (int i = 1; i < N; ++i) {
+        const int p = topo->parent[i];
+        if (p < 0 || p >= i) { set_error("link %d: parent %d violates topological order", i, p); return DRMB200_EINVAL; }
+        const int ax = topo->axis[i];
+        if (ax < -3 || ax > 3) { set_error("link %d: bad axis code %d", i, ax); return DRMB200_EINVAL; }
+        if (ax != 0 && (topo->dof[i] < 0 || topo->dof[i] >= topo->n_dofs)) { set_error("link %d: bad dof %d", i, (int)topo->dof[i]); return DRMB200_EINVAL; }
+        prog->parent[i] = (int8_t)p;
+        prog->axis[i] = (int8_t)ax;
+        prog->dof[i] = topo->dof[i];
+        if (p != i - 1 && p != 0) last_far_child[p] = i;
+    }
+    prog->parent[0] = -1; prog->axis[0] = 0; prog->dof[0] = -1; prog->psrc[0] = -1; prog->save[0] = -1;
+    int slot_of[DRMB200_MAX_LINKS];
+    int slot_free_after[DRM_MAX_SLOTS];
+    for (int s = 0; s < DRM_MAX_SLOTS; ++s) slot_free_after[s] = -1;
+    int n_slots = 0;
+    for (int i = 1; i < N; ++i) {
+        const int p = topo->parent[i];
+        prog->psrc[i] = (p == 0) ? -1 : (p == i - 1 ? 0 : (int8_t)(1 + slot_of[p]));
+        prog->save[i] = -1;
+        if (last_far_child[i] >= 0) {
+            int s = 0;
+            while (s < DRM_MAX_SLOTS && slot_free_after[s] >= i) ++s;
+            if (s == DRM_MAX_SLOTS) { set_error("tree needs more than %d live branch points", DRM_MAX_SLOTS); return DRMB200_ELIMIT; }
+            slot_of[i] = s;
+            slot_free_after[s] = last_far_child[i];
+            prog->save[i] = (int8_t)s;
+            if (s + 1 > n_slots) n_slots = s + 1;
+        }
+    }
+    prog->n_slots = n_slots;
+    return DRMB200_OK;
+}
+
+int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                            const float* qdd, int64_t batch, uint32_t flags, float* tau, cudaStream_t stream) {
+    TreeProgram prog;
+    int rc = build_tree_program(topo, &prog);
+    if (rc != DRMB200_OK) return rc;
+    if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
+    if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
+    if (table == nullptr || q == nullptr || qd == nullptr || qdd == nullptr || tau == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    const int64_t tiles = (batch + RNEA_TILE - 1) / RNEA_TILE;
+    if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
+
+    RneaArgs args;
+    args.table = table; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    args.bulk_ok = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
+
+    const RneaSmemLayout L(prog.n_dofs, prog.n_links, prog.n_slots);
+    const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
+    if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
+    static size_t configured_by_dev[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t& configured = configured_by_dev[dev & 63];
+    if (smem_bytes > configured) {
+        cudaError_t e = cudaFuncSetAttribute(rnea_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
+        configured = smem_bytes;
+    }
+    rnea_kernel<<<(unsigned)tiles, RNEA_TILE, smem_bytes, stream>>>(prog, args);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("rnea launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
+    count_launch();
+    return DRMB200_OK;
+}
+
+}  // namespace drm

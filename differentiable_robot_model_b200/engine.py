@@ -1,0 +1,223 @@
+"""
+ctypes binding of the C-ABI library + torch.autograd plumbing
+================================================================
+``libdrm_b200.so`` (``csrc/``, declared in ``include/drm_b200.h``) is the product: hand-written
+sm_100a kernels behind an ``extern "C"`` interface with plain pointers.  This module loads it with
+ctypes (no torch types cross the boundary -- only ``tensor.data_ptr()`` and the raw handle of the
+current CUDA stream) and wraps the forward / backward entry points in ``torch.autograd.Function``s so
+that the reference's parameter-learning examples keep training.
+
+There is NO fallback: if the library is missing, or tensors are not on a CUDA device, every
+compute entry raises ``RuntimeError``.
+"""
+import ctypes
+import os
+
+import torch
+
+from .link_table import Topology
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libdrm_b200.so")
+_lib = None
+
+GRAVITY = 1
+DAMPING = 2
+
+_c_float_p = ctypes.c_void_p      # raw device / host addresses
+_SIGNATURES = {
+    "drmb200_version": (ctypes.c_int, []),
+    "drmb200_last_error": (ctypes.c_char_p, []),
+    "drmb200_launch_count": (ctypes.c_int64, []),
+    "drmb200_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "drmb200_fk_jacobian": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, _c_float_p, _c_float_p,
+                                           ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                           ctypes.c_void_p]),
+    "drmb200_table_grad_workspace_bytes": (ctypes.c_int64, [ctypes.POINTER(Topology), ctypes.c_int64]),
+    "drmb200_fk_jacobian_backward": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, _c_float_p, _c_float_p,
+                                                    ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                    _c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "drmb200_inverse_dynamics": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
+                                                _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
+                                                ctypes.c_void_p]),
+    "drmb200_inverse_dynamics_backward": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
+                                                         _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
+                                                         _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                         ctypes.c_void_p, ctypes.c_void_p]),
+    "drmb200_fk_jacobian_host": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, ctypes.c_int32, _c_float_p,
+                                                _c_float_p, ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p,
+                                                _c_float_p]),
+}
+
+
+def library_path():
+    return _LIB_PATH
+
+
+def declared_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib():
+    """Load (once) and return the C-ABI library; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} not found: the B200 CUDA engine has not been built "
+                "(run `python -c 'import __graft_entry__ as g; g.build()'` or `make -C "
+                "differentiable_robot_model_b200/csrc`). There is no CPU fallback."
+            )
+        handle = ctypes.CDLL(_LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError if the library lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = handle
+    return _lib
+
+
+def _check(rc, what):
+    if rc != 0:
+        msg = lib().drmb200_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(
+                "the B200 engine computes on CUDA tensors only (got a tensor on "
+                f"{t.device}); there is no CPU fallback"
+            )
+        if t.dtype != torch.float32:
+            raise RuntimeError(f"the engine is fp32-only like the reference (got {t.dtype})")
+
+
+def launch_count():
+    return int(lib().drmb200_launch_count())
+
+
+def set_option(name, value):
+    _check(lib().drmb200_set_option(name.encode(), int(value)), "drmb200_set_option")
+
+
+# ------------------------------------------------------------------------------------------------
+# raw (non-differentiable) launches
+# ------------------------------------------------------------------------------------------------
+def fk_jacobian_raw(topo, ee_link, table, q, want_pos=True, want_quat=True, want_jac=True, out=None):
+    _require_cuda(table, q)
+    q = q.contiguous()
+    B, n = q.shape
+    dev = q.device
+    if out is not None:
+        pos, quat, jlin, jang = out
+    else:
+        pos = torch.empty((B, 3), device=dev, dtype=torch.float32) if want_pos else None
+        quat = torch.empty((B, 4), device=dev, dtype=torch.float32) if want_quat else None
+        jlin = torch.empty((B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
+        jang = torch.empty((B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
+    with torch.cuda.device(dev):
+        rc = lib().drmb200_fk_jacobian(ctypes.byref(topo), ee_link, _ptr(table), _ptr(q), B, _ptr(pos), _ptr(quat),
+                                       _ptr(jlin), _ptr(jang), _stream())
+    _check(rc, "drmb200_fk_jacobian")
+    return pos, quat, jlin, jang
+
+
+def inverse_dynamics_raw(topo, table, q, qd, qdd, flags, out=None):
+    _require_cuda(table, q, qd, qdd)
+    q, qd, qdd = q.contiguous(), qd.contiguous(), qdd.contiguous()
+    B, n = q.shape
+    tau = out if out is not None else torch.empty((B, n), device=q.device, dtype=torch.float32)
+    with torch.cuda.device(q.device):
+        rc = lib().drmb200_inverse_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B,
+                                            flags, _ptr(tau), _stream())
+    _check(rc, "drmb200_inverse_dynamics")
+    return tau
+
+
+def fk_jacobian_host(topo, ee_link, device_index, table, q_host, pos, quat, jlin, jang):
+    """Host-buffer FK+Jacobian (H2D / kernel / D2H pipelined inside the library)."""
+    _require_cuda(table)
+    B = q_host.shape[0]
+    rc = lib().drmb200_fk_jacobian_host(ctypes.byref(topo), ee_link, device_index, _ptr(table), _ptr(q_host), B,
+                                        _ptr(pos), _ptr(quat), _ptr(jlin), _ptr(jang))
+    _check(rc, "drmb200_fk_jacobian_host")
+
+
+def _workspace(topo, batch, device):
+    nbytes = int(lib().drmb200_table_grad_workspace_bytes(ctypes.byref(topo), batch))
+    return torch.empty((max(nbytes, 4) + 3) // 4, device=device, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# autograd
+# ------------------------------------------------------------------------------------------------
+class FkJacobianFunction(torch.autograd.Function):
+    """(table, q) -> (pos, quat, jac_lin, jac_ang); analytic backward kernel."""
+
+    @staticmethod
+    def forward(ctx, table, q, topo, ee_link, want_pos, want_quat, want_jac):
+        pos, quat, jlin, jang = fk_jacobian_raw(topo, ee_link, table, q, want_pos, want_quat, want_jac)
+        ctx.save_for_backward(table, q)
+        ctx.topo, ctx.ee_link = topo, ee_link
+        outs = (pos, quat, jlin, jang)
+        ctx.mark_non_differentiable(*[o for o in outs if o is None])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pos, g_quat, g_jlin, g_jang):
+        table, q = ctx.saved_tensors
+        need_table, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        B, n = q.shape
+        g = [None if t is None else t.contiguous() for t in (g_pos, g_quat, g_jlin, g_jang)]
+        _require_cuda(*g)
+        q_grad = torch.empty_like(q) if need_q else None
+        table_grad = torch.zeros_like(table) if need_table else None
+        ws = _workspace(ctx.topo, B, q.device)
+        with torch.cuda.device(q.device):
+            rc = lib().drmb200_fk_jacobian_backward(ctypes.byref(ctx.topo), ctx.ee_link, _ptr(table), _ptr(q), B,
+                                                    _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _ptr(q_grad),
+                                                    _ptr(table_grad), _ptr(ws), _stream())
+        _check(rc, "drmb200_fk_jacobian_backward")
+        return table_grad, q_grad, None, None, None, None, None
+
+
+class InverseDynamicsFunction(torch.autograd.Function):
+    """(table, q, qd, qdd) -> tau; analytic RNEA adjoint kernel."""
+
+    @staticmethod
+    def forward(ctx, table, q, qd, qdd, topo, flags):
+        tau = inverse_dynamics_raw(topo, table, q, qd, qdd, flags)
+        ctx.save_for_backward(table, q, qd, qdd)
+        ctx.topo, ctx.flags = topo, flags
+        return tau
+
+    @staticmethod
+    def backward(ctx, g_tau):
+        table, q, qd, qdd = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        B, n = q.shape
+        g_tau = g_tau.contiguous()
+        _require_cuda(g_tau)
+        table_grad = torch.zeros_like(table) if need[0] else None
+        q_grad = torch.empty_like(q) if need[1] else None
+        qd_grad = torch.empty_like(q) if need[2] else None
+        qdd_grad = torch.empty_like(q) if need[3] else None
+        ws = _workspace(ctx.topo, B, q.device)
+        with torch.cuda.device(q.device):
+            rc = lib().drmb200_inverse_dynamics_backward(
+                ctypes.byref(ctx.topo), _ptr(table), _ptr(q.contiguous()), _ptr(qd.contiguous()),
+                _ptr(qdd.contiguous()), B, ctx.flags, _ptr(g_tau), _ptr(q_grad), _ptr(qd_grad), _ptr(qdd_grad),
+                _ptr(table_grad), _ptr(ws), _stream())
+        _check(rc, "drmb200_inverse_dynamics_backward")
+        return table_grad, q_grad, qd_grad, qdd_grad, None, None

@@ -1,0 +1,130 @@
+"""
+Model compiler: per-link host objects -> flat tables for the CUDA kernels
+==========================================================================
+Two products (layout documented in ``include/drm_b200.h``):
+
+* ``Topology`` -- immutable integers (parent index, joint-axis code, DoF column per link), resolved
+  ONCE at model construction.  The reference re-resolves parents by *name* with an O(#joints) scan
+  inside every per-link loop (``robot_model.py:176,264,297,563,606,664``).
+* ``build_link_table`` -- the differentiable float table ``[n_links, 28]`` on the model's device,
+  built with ordinary (batched) torch ops from whatever the six per-link parameter callables
+  return, so autograd carries the kernels' ``d table`` back to any user parametrisation module
+  (``robot_model.py:682-689``).  Contents per link: ``F = Rz(yaw) Ry(pitch) Rx(roll)``
+  (``rigid_body.py:138-143``), ``r = trans``, ``I_o = I_c + m S(c) S(c)^T`` and ``mc = m c``
+  (``spatial_vector_algebra.py:323-327``; ``inertia_mat`` is used as given, NOT symmetrised),
+  ``m``, ``damping``.  The reference recomputes all of these for every link on every call.
+"""
+import ctypes
+
+import torch
+
+MAX_LINKS = 64        # DRMB200_MAX_LINKS
+TABLE_STRIDE = 28     # DRMB200_TABLE_STRIDE
+
+
+class Topology(ctypes.Structure):
+    """ctypes mirror of ``drmb200_topology_t`` (include/drm_b200.h)."""
+
+    _fields_ = [
+        ("n_links", ctypes.c_int32),
+        ("n_dofs", ctypes.c_int32),
+        ("parent", ctypes.c_int8 * MAX_LINKS),
+        ("axis", ctypes.c_int8 * MAX_LINKS),
+        ("dof", ctypes.c_int8 * MAX_LINKS),
+    ]
+
+
+def axis_code(joint_axis, joint_name=""):
+    """Signed axis code (+-1/+-2/+-3 = +-x/+-y/+-z) of a movable joint.
+
+    The reference dispatches on ``|axis[k]| == 1`` (``rigid_body.py:149-154``) and is inconsistent for
+    anything else (FK silently falls through to z, inverse dynamics raises, ``robot_model.py:357``);
+    every shipped URDF uses signed coordinate axes, so anything else is rejected here.
+    """
+    a = [float(x) for x in joint_axis.reshape(-1).tolist()]
+    nz = [k for k in range(3) if a[k] != 0.0]
+    if len(nz) != 1 or abs(a[nz[0]]) != 1.0:
+        raise ValueError(
+            f"joint {joint_name!r}: axis {a} is not a signed coordinate axis; only +-x / +-y / +-z "
+            "joint axes are supported (the reference is inconsistent for other axes)"
+        )
+    k = nz[0]
+    return (k + 1) if a[k] > 0 else -(k + 1)
+
+
+def compile_topology(bodies, parent_idx):
+    n_links = len(bodies)
+    if n_links > MAX_LINKS:
+        raise ValueError(f"{n_links} links exceed the engine limit of {MAX_LINKS}")
+    topo = Topology()
+    topo.n_links = n_links
+    n_dofs = 0
+    for i, body in enumerate(bodies):
+        p = parent_idx[i]
+        if i == 0:
+            p = -1
+        elif not (0 <= p < i):
+            raise ValueError(
+                f"link {body.name!r} (index {i}) has parent index {p}: links must be listed parents-first "
+                "(true for every shipped URDF; the reference assumes link 0 is the root)"
+            )
+        topo.parent[i] = p
+        if body.joint_idx is not None:
+            topo.axis[i] = axis_code(body.joint_axis, body.name)
+            topo.dof[i] = body.joint_idx
+            n_dofs += 1
+        else:
+            topo.axis[i] = 0
+            topo.dof[i] = -1
+    topo.n_dofs = n_dofs
+    return topo
+
+
+def _rpy_to_matrix(rpy):
+    """Batched ``Rz(yaw) @ Ry(pitch) @ Rx(roll)`` for rpy ``[N,3]`` (rigid_body.py:138-143)."""
+    cr, sr = torch.cos(rpy[:, 0]), torch.sin(rpy[:, 0])
+    cp, sp = torch.cos(rpy[:, 1]), torch.sin(rpy[:, 1])
+    cy, sy = torch.cos(rpy[:, 2]), torch.sin(rpy[:, 2])
+    rows = [
+        cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+        sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+        -sp, cp * sr, cp * cr,
+    ]
+    return torch.stack(rows, dim=1)          # [N, 9] row-major
+
+
+def build_link_table(bodies, device):
+    """Evaluate every link's parameter callables into the ``[n_links, 28]`` fp32 device table."""
+    f32 = dict(dtype=torch.float32, device=device)
+    trans, rpy, mass, com, inertia, damping = [], [], [], [], [], []
+    for i, body in enumerate(bodies):
+        movable = body.joint_idx is not None
+        # fixed joints keep their construction-time origin (reference quirk, rigid_body.py:64-67)
+        trans.append((body.trans() if movable else body._ctor_trans).reshape(3))
+        rpy.append((body.rot_angles() if movable else body._ctor_rot_angles).reshape(3))
+        m, c, inert = body.inertia._get_parameter_values()
+        mass.append(m.reshape(()))
+        com.append(c.reshape(3))
+        inertia.append(inert.reshape(9))
+        d = body.joint_damping() if movable else None
+        damping.append(d.reshape(()) if d is not None else torch.zeros((), **f32))
+    trans = torch.stack(trans).to(**f32)
+    rpy = torch.stack(rpy).to(**f32)
+    mass = torch.stack(mass).to(**f32)
+    com = torch.stack(com).to(**f32)
+    inertia = torch.stack(inertia).to(**f32)
+    damping = torch.stack(damping).to(**f32)
+
+    F = _rpy_to_matrix(rpy)
+    cx, cy, cz = com[:, 0], com[:, 1], com[:, 2]
+    # S(c) S(c)^T = |c|^2 I - c c^T
+    ssT = torch.stack(
+        [cy * cy + cz * cz, -cx * cy, -cx * cz,
+         -cx * cy, cx * cx + cz * cz, -cy * cz,
+         -cx * cz, -cy * cz, cx * cx + cy * cy], dim=1)
+    Io = inertia + mass[:, None] * ssT
+    mc = mass[:, None] * com
+    pad = torch.zeros((len(bodies), 2), **f32)
+    table = torch.cat([F, trans, Io, mc, mass[:, None], damping[:, None], pad], dim=1)
+    assert table.shape == (len(bodies), TABLE_STRIDE)
+    return table.contiguous()

@@ -1,0 +1,75 @@
+"""
+Per-link host objects
+====================================
+Host-side mirror of the reference's ``DifferentiableRigidBody`` (``rigid_body.py:24-171``) and
+``DifferentiableSpatialRigidBodyInertia`` (``spatial_vector_algebra.py:308-372``).
+
+In the reference these objects *compute*: every call of ``update_joint_state`` builds ``[B,3,3]``
+tensors per link.  Here they only *hold parameters*: the six attributes that can be made learnable
+(``trans``, ``rot_angles``, ``joint_damping`` on the body; ``mass``, ``com``, ``inertia_mat`` on
+``body.inertia``) are zero-argument callables -- plain lambdas over the URDF constants, or the
+``torch.nn.Module`` a caller swapped in through ``make_link_param_learnable``
+(``robot_model.py:682-689``).  ``link_table.build_link_table`` evaluates them once per call into the
+flat device table the CUDA kernels read; all per-configuration arithmetic happens in the kernels.
+"""
+from typing import List, Optional
+
+import torch
+
+
+class DifferentiableSpatialRigidBodyInertia(torch.nn.Module):
+    def __init__(self, rigid_body_params, device="cpu"):
+        super().__init__()
+        self.mass = lambda: rigid_body_params["mass"]
+        self.com = lambda: rigid_body_params["com"]
+        self.inertia_mat = lambda: rigid_body_params["inertia_mat"]
+        self._device = torch.device(device)
+
+    def _get_parameter_values(self):
+        return self.mass(), self.com(), self.inertia_mat()
+
+
+class DifferentiableRigidBody(torch.nn.Module):
+    """One link plus the joint that connects it to its parent (joint at the start of the link)."""
+
+    _children: List["DifferentiableRigidBody"]
+
+    def __init__(self, rigid_body_params, device="cpu"):
+        super().__init__()
+        # plain (unregistered) references: registering the parent as a sub-module would create
+        # module cycles and duplicate state_dict entries
+        object.__setattr__(self, "_parent", None)
+        object.__setattr__(self, "_children", [])
+        self._device = torch.device(device)
+        self.joint_id = rigid_body_params["joint_id"]
+        self.name = rigid_body_params["link_name"]
+        self.joint_type = rigid_body_params["joint_type"]
+        self.joint_idx = None          # DoF column, assigned by the model for movable joints
+
+        # parameters that can be made learnable
+        self.inertia = DifferentiableSpatialRigidBodyInertia(rigid_body_params, device=self._device)
+        self.joint_damping = lambda: rigid_body_params["joint_damping"]
+        self.trans = lambda: rigid_body_params["trans"].reshape(1, 3)
+        self.rot_angles = lambda: rigid_body_params["rot_angles"].reshape(1, 3)
+
+        self.joint_axis = rigid_body_params["joint_axis"]
+        self.joint_limits = rigid_body_params["joint_limits"]
+
+        # The reference builds the joint pose of a *fixed* joint once, in the constructor
+        # (rigid_body.py:64-67); making its trans / rot_angles learnable later has no effect.
+        # Keep the construction-time values so the link table reproduces that behaviour.
+        self._ctor_trans = rigid_body_params["trans"].reshape(1, 3).detach().clone()
+        self._ctor_rot_angles = rigid_body_params["rot_angles"].reshape(1, 3).detach().clone()
+
+    # kinematic tree construction (robot_model.py:133-137)
+    def set_parent(self, link: "DifferentiableRigidBody"):
+        object.__setattr__(self, "_parent", link)
+
+    def add_child(self, link: "DifferentiableRigidBody"):
+        self._children.append(link)
+
+    def get_joint_limits(self):
+        return self.joint_limits
+
+    def get_joint_damping_const(self):
+        return self.joint_damping()

@@ -1,0 +1,144 @@
+/*
+ * drm_b200.h -- C ABI of the B200-native batched rigid-body kinematics/dynamics engine.
+ *
+ * This is the drop-in boundary for the hot path of facebookresearch/differentiable-robot-model
+ * (reference paths below are relative to /root/reference):
+ *
+ *   drmb200_fk_jacobian        replaces  DifferentiableRobotModel.compute_forward_kinematics
+ *                                        (differentiable_robot_model/robot_model.py:224-248) and
+ *                                        compute_endeffector_jacobian (robot_model.py:627-667),
+ *                                        i.e. update_kinematic_state (robot_model.py:140-195) +
+ *                                        CoordinateTransform.get_quaternion
+ *                                        (spatial_vector_algebra.py:108-136) in one launch.
+ *   drmb200_fk_jacobian_backward         the analytic adjoint of the above (the reference relies on
+ *                                        autograd over its per-link op graph; no single line).
+ *   drmb200_inverse_dynamics   replaces  compute_inverse_dynamics (robot_model.py:306-375) =
+ *                                        update_kinematic_state + iterative_newton_euler
+ *                                        (robot_model.py:251-303) + axis projection + damping.
+ *   drmb200_inverse_dynamics_backward    analytic adjoint of RNEA.
+ *   drmb200_fk_jacobian_host   the same FK+Jacobian op on HOST buffers (pinned or pageable):
+ *                              chunked H2D -> kernel -> D2H pipeline on internal streams.
+ *
+ * The reference has no FFI of its own (it is pure Python); the reference-side binding is the
+ * ctypes stub shown in INTEGRATION.md.  All entry points are `extern "C"`, take plain pointers
+ * and sizes, never throw, never synchronise the device (except the *_host variants, which return
+ * after their last D2H copy completed) and return 0 on success or a negative DRMB200_E* code.
+ *
+ * Data layout (all fp32, contiguous, row-major; the reference is fp32-only):
+ *   q, qd, qdd, tau      [B, n_dofs]
+ *   pos                  [B, 3]
+ *   quat                 [B, 4]    xyzw, branch structure of spatial_vector_algebra.py:116-135
+ *   jac_lin, jac_ang     [B, 3, n_dofs]
+ *   table                [n_links, DRMB200_TABLE_STRIDE]  the differentiable link table, device
+ *                        memory, one row per link in URDF document order:
+ *        [0:9)   F      fixed joint rotation Rz(yaw)Ry(pitch)Rx(roll), row-major (rigid_body.py:138-143)
+ *        [9:12)  r      joint origin translation                       (rigid_body.py:146)
+ *        [12:21) I_o    rotational inertia about the link origin, row-major, NOT symmetrised
+ *                       I_c + m S(c)S(c)^T                             (spatial_vector_algebra.py:324-327)
+ *        [21:24) mc     mass * centre of mass                          (spatial_vector_algebra.py:323)
+ *        [24]    m      mass
+ *        [25]    d      joint damping                                  (robot_model.py:368-373)
+ *        [26:28) pad
+ *   table_grad           same shape; batch-summed adjoint of every table entry.
+ */
+#ifndef DRM_B200_H
+#define DRM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRMB200_MAX_LINKS 64
+#define DRMB200_TABLE_STRIDE 28
+
+/* status codes */
+#define DRMB200_OK 0
+#define DRMB200_EINVAL (-1)   /* null pointer, negative batch, bad link index, bad topology */
+#define DRMB200_ECUDA (-2)    /* CUDA runtime error; see drmb200_last_error() */
+#define DRMB200_ELIMIT (-3)   /* model exceeds DRMB200_MAX_LINKS */
+
+/* flags for the dynamics entry points (robot_model.py:311-312) */
+#define DRMB200_GRAVITY 1u    /* include_gravity: base linear acceleration (0, 0, +9.81) */
+#define DRMB200_DAMPING 2u    /* use_damping: tau += damping * qd */
+
+/*
+ * Immutable kinematic-tree topology, host memory, links in URDF document order
+ * (= reference body index order, robot_model.py:114).  parent[i] < i for every i > 0 is required
+ * (all shipped URDFs satisfy it; the host loader checks).
+ */
+typedef struct drmb200_topology {
+    int32_t n_links;
+    int32_t n_dofs;
+    int8_t parent[DRMB200_MAX_LINKS]; /* -1 for the root (link 0)                              */
+    int8_t axis[DRMB200_MAX_LINKS];   /* 0 fixed; +-1 / +-2 / +-3 = revolute about +-x / +-y / +-z */
+    int8_t dof[DRMB200_MAX_LINKS];    /* column in q / tau / Jacobian, -1 for fixed joints      */
+} drmb200_topology_t;
+
+/* Library / build introspection. */
+int drmb200_version(void);                 /* 10000*major + 100*minor + patch */
+const char* drmb200_last_error(void);      /* thread-local text of the last failure */
+int64_t drmb200_launch_count(void);        /* kernels launched by this library since load */
+/* Tuning knobs for A/B measurements (not part of the reference-facing surface):
+ *   "fk_variant": 1 = TMA bulk-copy staging (default), 0 = cooperative float4 staging. */
+int drmb200_set_option(const char* name, int value);
+
+/*
+ * FK (+ geometric Jacobian) of link `ee_link` for a batch of joint configurations.
+ * Any of pos / quat / (jac_lin, jac_ang) may be NULL to skip that output (jac_lin and jac_ang
+ * must be both NULL or both non-NULL).  Columns of joints that are not on the ee->root path are
+ * written as zeros (robot_model.py:646-649).  Device pointers; asynchronous on `cuda_stream`.
+ */
+int drmb200_fk_jacobian(const drmb200_topology_t* topo, int32_t ee_link,
+                        const float* table, const float* q, int64_t batch,
+                        float* pos, float* quat, float* jac_lin, float* jac_ang,
+                        void* cuda_stream);
+
+/*
+ * Adjoint of drmb200_fk_jacobian.  g_* are the upstream gradients of the corresponding outputs
+ * (NULL = zero).  Writes q_grad [B, n_dofs] (may be NULL) and accumulates the batch-summed
+ * gradient of the table into table_grad [n_links, 28] (may be NULL; must be zero-initialised or
+ * hold a running sum).  `workspace` must hold drmb200_fk_jacobian_backward_workspace() bytes.
+ */
+int64_t drmb200_table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch);
+int drmb200_fk_jacobian_backward(const drmb200_topology_t* topo, int32_t ee_link,
+                                 const float* table, const float* q, int64_t batch,
+                                 const float* g_pos, const float* g_quat,
+                                 const float* g_jac_lin, const float* g_jac_ang,
+                                 float* q_grad, float* table_grad,
+                                 void* workspace, void* cuda_stream);
+
+/*
+ * Recursive Newton-Euler inverse dynamics, tau [B, n_dofs].  flags = DRMB200_GRAVITY | DRMB200_DAMPING.
+ */
+int drmb200_inverse_dynamics(const drmb200_topology_t* topo,
+                             const float* table, const float* q, const float* qd, const float* qdd,
+                             int64_t batch, uint32_t flags, float* tau, void* cuda_stream);
+
+/*
+ * Adjoint of drmb200_inverse_dynamics given g_tau [B, n_dofs].  Any of q_grad / qd_grad / qdd_grad
+ * [B, n_dofs] and table_grad [n_links, 28] may be NULL.
+ */
+int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo,
+                                      const float* table, const float* q, const float* qd,
+                                      const float* qdd, int64_t batch, uint32_t flags,
+                                      const float* g_tau,
+                                      float* q_grad, float* qd_grad, float* qdd_grad,
+                                      float* table_grad, void* workspace, void* cuda_stream);
+
+/*
+ * Host-buffer variant of drmb200_fk_jacobian: q and the outputs are HOST pointers (pinned memory
+ * gives full PCIe bandwidth; pageable memory works).  `table` is still a device pointer (it is
+ * < 8 KB and lives with the model).  The call splits the batch into chunks, overlaps
+ * H2D / kernel / D2H on internal streams of `device`, and returns once all outputs are on the host.
+ */
+int drmb200_fk_jacobian_host(const drmb200_topology_t* topo, int32_t ee_link, int32_t device,
+                             const float* table, const float* q_host, int64_t batch,
+                             float* pos_host, float* quat_host,
+                             float* jac_lin_host, float* jac_ang_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRM_B200_H */

@@ -1,0 +1,124 @@
+"""CPU: pin oracle/drm_oracle.py against the golden vectors generated from the reference itself
+(tests/golden/make_golden.py) and against the known answers of SURVEY.md section 8(c)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, canon_quat, load_golden, urdf_path
+from oracle import drm_oracle as O
+
+
+def _inputs(g, dtype):
+    return tuple(torch.tensor(g[k], dtype=dtype) for k in ("q", "qd", "qdd"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_oracle_matches_reference_forward(robot_stem, dtype):
+    g = load_golden(robot_stem)
+    robot = O.load_robot(urdf_path(robot_stem), dtype)
+    q, qd, qdd = _inputs(g, dtype)
+
+    # parsed link parameters are bit-identical to what the reference parsed
+    for key, mine in (("trans", robot.trans), ("rpy", robot.rpy), ("axis", robot.axis), ("mass", robot.mass),
+                      ("com", robot.com), ("inertia", robot.inertia), ("damping", robot.damping)):
+        np.testing.assert_array_equal(mine.to(torch.float32).numpy(), g[key], err_msg=key)
+    assert robot.parent == g["parent"].tolist() and robot.dof == g["dof"].tolist()
+    assert robot.names == g["link_names"].tolist()
+
+    R, p, _, _, _ = O.kinematic_state(robot, q, qd)
+    assert_close(torch.stack(R).numpy(), g["all_R"], what="all-link rotations")
+    assert_close(torch.stack(p).numpy(), g["all_p"], what="all-link positions")
+    for link in g["fk_links"].tolist():
+        pos, quat = O.forward_kinematics(robot, q, link)
+        assert_close(pos.numpy(), g[f"pos.{link}"], what=f"pos {link}")
+        assert_close(canon_quat(quat.numpy()), canon_quat(g[f"quat.{link}"]), what=f"quat {link}")
+        jl, ja = O.jacobian(robot, q, link)
+        assert_close(jl.numpy(), g[f"jlin.{link}"], what=f"jlin {link}")
+        assert_close(ja.numpy(), g[f"jang.{link}"], what=f"jang {link}")
+    for grav in (0, 1):
+        for damp in (0, 1):
+            tau = O.inverse_dynamics(robot, q, qd, qdd, bool(grav), bool(damp))
+            # the reference's own inverse-dynamics tolerance is atol=1e-5 (tests/test_kinematics_dynamics.py:373-377)
+            assert_close(tau.numpy(), g[f"tau.g{grav}d{damp}"], rtol=1e-5, atol=1e-5, what=f"tau g{grav} d{damp}")
+
+
+def test_oracle_raw_quaternion_sign_matches_reference(robot_stem):
+    """Away from branch boundaries even the raw (non-canonicalised) sign convention must agree."""
+    g = load_golden(robot_stem)
+    robot = O.load_robot(urdf_path(robot_stem), torch.float32)
+    q = torch.tensor(g["q"])
+    for link in g["fk_links"].tolist():
+        _, quat = O.forward_kinematics(robot, q, link)
+        ref = g[f"quat.{link}"]
+        same = np.abs(quat.numpy() - ref).max(axis=1) < 1e-5
+        assert same.mean() >= 0.85, f"{link}: raw quaternion sign differs on {np.sum(~same)} of {len(same)} rows"
+
+
+def _grad_robot(stem, dtype):
+    robot = O.load_robot(urdf_path(stem), dtype)
+    for name in ("trans", "rpy", "mass", "com", "inertia", "damping"):
+        getattr(robot, name).requires_grad_(True)
+    return robot
+
+
+def test_oracle_gradients_match_reference_autograd(robot_stem):
+    """fp64 oracle + torch autograd vs the gradients of the reference's own fp32 autograd graph."""
+    g = load_golden(robot_stem)
+    dt = torch.float64
+    q, qd, qdd = (t.requires_grad_(True) for t in _inputs(g, dt))
+    G = {k: torch.tensor(g[k], dtype=dt) for k in ("G_pos", "G_jl", "G_ja", "G_tau")}
+    param_of = {"trans": "trans", "rot_angles": "rpy", "mass": "mass", "com": "com", "inertia_mat": "inertia",
+                "joint_damping": "damping"}
+
+    def check(prefix, robot, loss, inputs):
+        grads = torch.autograd.grad(loss, inputs + [robot.trans, robot.rpy, robot.mass, robot.com, robot.inertia,
+                                                    robot.damping], allow_unused=True)
+        n_in = len(inputs)
+        by_name = dict(zip(["trans", "rpy", "mass", "com", "inertia", "damping"], grads[n_in:]))
+        scale = max(float(np.abs(g[k]).max()) for k in g.files if k.startswith(prefix))
+        tol = dict(rtol=2e-4, atol=2e-5 * max(scale, 1.0))     # fp32 reference autograd noise
+        for t, key in zip(grads[:n_in], ("q", "qd", "qdd")):
+            assert_close(t.numpy(), g[f"{prefix}.{key}"], what=f"{prefix}.{key}", **tol)
+        checked = 0
+        for key in g.files:
+            if not key.startswith(prefix + "."):
+                continue
+            rest = key[len(prefix) + 1:]
+            if "." not in rest:
+                continue
+            pname, idx = rest.rsplit(".", 1)
+            if pname not in param_of:
+                continue
+            mine = by_name[param_of[pname]]
+            mine = torch.zeros_like(getattr(robot, param_of[pname])) if mine is None else mine
+            assert_close(mine[int(idx)].reshape(g[key].shape).numpy(), g[key], what=key, **tol)
+            checked += 1
+        assert checked > 0
+
+    for link in g["fk_links"].tolist()[:2]:
+        robot = _grad_robot(robot_stem, dt)
+        pos, _ = O.forward_kinematics(robot, q, link)
+        jl, ja = O.jacobian(robot, q, link)
+        check(f"fkgrad.{link}", robot, (G["G_pos"] * pos).sum() + (G["G_jl"] * jl).sum() + (G["G_ja"] * ja).sum(), [q])
+    robot = _grad_robot(robot_stem, dt)
+    tau = O.inverse_dynamics(robot, q, qd, qdd, True, True)
+    check("idgrad", robot, (G["G_tau"] * tau).sum(), [q, qd, qdd])
+
+
+def test_known_answers():
+    """Hand-checkable values quoted in SURVEY.md section 8(c) (Kuka, q_k = 0.1 k)."""
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float32)
+    k = torch.arange(1, 8, dtype=torch.float32)
+    q, qd, qdd = (0.1 * k)[None], (0.05 * k)[None], (-0.02 * k)[None]
+    pos, quat = O.forward_kinematics(robot, torch.zeros(1, 7), "iiwa_link_ee")
+    assert_close(pos.numpy(), [[0.0, 0.0, 1.266]], what="zero pose")
+    assert_close(quat.numpy(), [[0.0, 0.0, 0.0, 1.0]], what="zero quat")
+    pos, quat = O.forward_kinematics(robot, q, "iiwa_link_ee")
+    assert_close(pos.numpy(), [[0.03738306, -0.00471164, 1.2391480]], what="pos")
+    assert_close(quat.numpy(), [[-0.04092941, 0.19003928, 0.69464809, 0.69258499]], what="quat")
+    tau = O.inverse_dynamics(robot, q, qd, qdd, True, True)
+    assert_close(tau.numpy(), [[0.01269711, -8.3910265, -0.68258399, -4.2039914, 0.42146286, -1.0341269, 0.17390044]],
+                 atol=1e-5, what="tau")
+    tau = O.inverse_dynamics(robot, q, qd, qdd, False, False)
+    assert_close(tau.numpy(), [[-0.01230314, -0.09288787, -0.00786535, 0.03695315, -0.00435376, -0.00580134,
+                                -0.00109955]], atol=1e-5, what="tau no gravity")
