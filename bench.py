@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- FK + end-effector Jacobian throughput of the Kuka iiwa 7-DoF (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One *step* = one pass of the hot path (one `drmb200_fk_jacobian` launch: pos, quat, J_lin, J_ang
+of `iiwa_link_ee`) over one batch of 65 536 synthetic joint configurations (BASELINE.json
+configs[1]).  Inputs are resident in HBM before the timed region; the step cycles through ROTATE
+distinct buffer sets (> the 126 MB L2) so no launch finds its data in L2.  Launches are replayed from
+a CUDA graph (the per-launch Python/ctypes overhead would otherwise exceed the ~4 us kernel).
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+
+Extra keys on the JSON line (see DESIGN.md "Measurement"):
+  roofline            dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline_large_batch  the same kernel on 2^22 configurations per launch (the asymptotic figure)
+  e2e                 same metric through the host-buffer C-ABI call (H2D + kernel + D2H per step)
+  cpu_baseline        the CPU oracle port (oracle/drm_oracle.py, all host threads) on a bounded sample
+  clocks              nvidia-smi SM clocks / throttle reasons sampled during the timed region
+
+`--impl reference` times the reference's CPU implementation of the path: the reference is pure
+Python and cannot travel to the GPU box, so this arm runs the oracle port of its algorithm
+(batched torch ops per link, fp32, all host threads) -- rank 0 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+BATCH = 65536                 # BASELINE.json configs[1]
+EE_LINK = "iiwa_link_ee"
+N_DOF = 7
+BYTES_PER_CONFIG = 28 * N_DOF + 28      # 4n (q) + 12 (pos) + 16 (quat) + 24n (J_lin, J_ang) = 224
+ROTATE = 16                   # 16 x 14.7 MB = 235 MB of distinct buffers > 126 MB L2
+GRAPH_NODES = 512
+METRIC = "FK+Jacobian configs/sec (Kuka iiwa 7-DoF)"
+UNIT = "configs/s"
+
+
+def measured_peak_gbs():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons every 100 ms while the timed region runs."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.thread, self.t0, self.t1 = [], None, None, None, None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
+
+    def summary(self):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+        parsed = []
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                parsed.append((ts, float(parts[0]), float(parts[1]), parts[3:7]))
+            except ValueError:
+                continue
+        if not parsed:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "nvidia-smi unavailable"}
+        inside = [p for p in parsed if self.t0 is not None and self.t0 <= p[0] <= (self.t1 or 1e30) + 0.1]
+        use = inside if inside else parsed
+        clocks = sorted(p[1] for p in use)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({names[i] for p in use for i in range(4) if p[3][i].lower().startswith("active")})
+        return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": max(p[2] for p in use), "reasons": reasons,
+                "samples": len(use), "window": "timed region" if inside else "whole run (timed region < sampling period)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port (oracle) timing -- cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def time_cpu_port(batch, min_seconds, max_calls, warmup=1):
+    from oracle import drm_oracle as O
+    import differentiable_robot_model_b200 as drm
+    torch.set_num_threads(os.cpu_count() or 1)
+    urdf = drm.DifferentiableKUKAiiwa().urdf_path
+    robot = O.load_robot(urdf, torch.float32)
+    q, _, _ = O.sample_inputs(robot, batch, seed=0)
+
+    def call():
+        with torch.no_grad():
+            R, p, _, _, _ = O.kinematic_state(robot, q)
+            e = robot.index(EE_LINK)
+            quat = O.quaternion(R[e])
+            lin, ang = O.jacobian(robot, q, EE_LINK)
+        return p[e], quat, lin, ang
+
+    for _ in range(warmup):
+        call()
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_calls and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
+        t0 = time.perf_counter()
+        call()
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # bounded sample per step so that steps + warmup finish within ~2 minutes
+    probe = time_cpu_port(4096, 0.0, 3)
+    per_cfg = sorted(probe)[len(probe) // 2] / 4096
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    batch = int(max(256, min(BATCH, budget / per_cfg)))
+    times = time_cpu_port(batch, 0.0, args.steps, warmup=max(1, min(args.warmup, 3)))
+    total = sum(times)
+    value = batch * len(times) / total
+    cores = os.cpu_count() or 1
+    sample = (f"{len(times)} steps x {batch} Kuka FK+Jacobian configurations through oracle/drm_oracle.py "
+              f"(torch CPU port of the reference's per-link algorithm, fp32, vectorised quaternion), {cores} threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Kuka iiwa 7-DoF FK + end-effector Jacobian (BASELINE.json configs[1])",
+                   "batch_per_step": batch, "ee_link": EE_LINK},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200000)
+    ap.add_argument("--warmup", type=int, default=2000)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-large", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch.distributed as dist
+    import differentiable_robot_model_b200 as drm
+    from differentiable_robot_model_b200 import engine, parallel
+    from oracle import drm_oracle as O
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model = drm.DifferentiableKUKAiiwa(device=dev)
+    table = model._link_table()
+    if world > 1:
+        table = parallel.broadcast_link_table(model)        # the single NCCL broadcast of the data path
+    topo, ee = model._topology, model._name_to_idx_map[EE_LINK]
+
+    # ---- synthetic inputs, per-rank seed, resident in HBM ------------------------------------------
+    robot = O.load_robot(model.urdf_path, torch.float32)
+    qs, outs = [], []
+    for r in range(ROTATE):
+        q, _, _ = O.sample_inputs(robot, BATCH, seed=1000 * rank + r)
+        qs.append(q.to(dev))
+        outs.append((torch.empty(BATCH, 3, device=dev), torch.empty(BATCH, 4, device=dev),
+                     torch.empty(BATCH, 3, N_DOF, device=dev), torch.empty(BATCH, 3, N_DOF, device=dev)))
+
+    def step(i):
+        engine.fk_jacobian_raw(topo, ee, table, qs[i % ROTATE], out=outs[i % ROTATE])
+
+    stream = torch.cuda.Stream(device=dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    with torch.cuda.stream(stream):
+        for i in range(min(args.warmup, 64)):
+            step(i)
+        stream.synchronize()
+        nodes = max(1, min(GRAPH_NODES, args.steps))
+        nodes -= nodes % ROTATE if nodes >= ROTATE else 0
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for i in range(nodes):
+                step(i)
+        replays, rest = divmod(args.steps, nodes)
+        for _ in range(max(1, (args.warmup - 64) // nodes)):
+            graph.replay()
+        stream.synchronize()
+
+        def barrier():
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize(dev)
+
+        launches_before = engine.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        if sampler:
+            sampler.mark_start()
+        ev0.record(stream)
+        for _ in range(replays):
+            graph.replay()
+        for i in range(rest):
+            step(i)
+        ev1.record(stream)
+        stream.synchronize()
+        if sampler:
+            sampler.mark_end()
+        barrier()
+        elapsed_ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    gpu_launches = replays * nodes + rest
+    assert engine.launch_count() - launches_before == rest       # graph replays bypass the library counter
+
+    value = world * args.steps * BATCH / (elapsed_ms * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    us_per_launch = elapsed_ms * 1e3 / args.steps
+    achieved = BATCH * BYTES_PER_CONFIG / (us_per_launch * 1e-6) / 1e9
+
+    result = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Kuka iiwa 7-DoF FK + end-effector Jacobian, batch 65536 per step per GPU "
+                               "(BASELINE.json configs[1])",
+                   "ee_link": EE_LINK, "batch_per_step_per_gpu": BATCH, "global_batch_per_step": BATCH * world,
+                   "parallelism": f"batch-sharded x{world}, no data-path collective",
+                   "l2_policy": f"rotating {ROTATE} distinct buffer sets ({ROTATE * BATCH * BYTES_PER_CONFIG / 1e6:.0f} MB) > L2",
+                   "launch": f"CUDA graph of {nodes} kernel nodes replayed {replays}x + {rest} direct launches"},
+        "gpu_launches": gpu_launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "fk_jacobian_kernel<WITH_JAC, TMA bulk>",
+                     "algorithmic_bytes_per_launch": BATCH * BYTES_PER_CONFIG, "us_per_launch": us_per_launch},
+    }
+
+    if rank == 0:
+        prof = os.path.join(REPO, "profiles", "fk_jacobian_traffic.json")
+        if os.path.exists(prof):
+            try:
+                result["roofline"]["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch_batch65536")
+            except Exception:
+                pass
+
+    # ---- asymptotic figure: 2^22 configurations per launch -----------------------------------------
+    if not args.no_large and rank == 0:
+        big = 1 << 22
+        del outs
+        torch.cuda.empty_cache()
+        q_big = torch.cat([qs[i % ROTATE] for i in range(big // BATCH)])
+        out_big = (torch.empty(big, 3, device=dev), torch.empty(big, 4, device=dev),
+                   torch.empty(big, 3, N_DOF, device=dev), torch.empty(big, 3, N_DOF, device=dev))
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                engine.fk_jacobian_raw(topo, ee, table, q_big, out=out_big)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            stream.synchronize()
+            reps = 20
+            e0.record(stream)
+            for _ in range(reps):
+                engine.fk_jacobian_raw(topo, ee, table, q_big, out=out_big)
+            e1.record(stream)
+            stream.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        ach = big * BYTES_PER_CONFIG / (ms * 1e-3) / 1e9
+        result["roofline_large_batch"] = {"batch_per_launch": big, "bytes_per_launch": big * BYTES_PER_CONFIG,
+                                          "ms_per_launch": ms, "configs_per_s": big / (ms * 1e-3), "achieved": ach,
+                                          "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                          "l2_policy": "0.94 GB per launch >> L2"}
+        del q_big, out_big
+        torch.cuda.empty_cache()
+
+    # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
+    if not args.no_e2e:
+        e2e_steps = max(3, min(args.steps, 200))
+        q_host = [qs[i].cpu().pin_memory() for i in range(2)]
+        host_out = [(torch.empty(BATCH, 3).pin_memory(), torch.empty(BATCH, 4).pin_memory(),
+                     torch.empty(BATCH, 3, N_DOF).pin_memory(), torch.empty(BATCH, 3, N_DOF).pin_memory())
+                    for _ in range(2)]
+        for i in range(3):
+            engine.fk_jacobian_host(topo, ee, local_rank, table, q_host[i % 2], *host_out[i % 2])
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            engine.fk_jacobian_host(topo, ee, local_rank, table, q_host[i % 2], *host_out[i % 2])
+        torch.cuda.synchronize(dev)
+        dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        result["e2e"] = {"value": world * e2e_steps * BATCH / float(dt.item()), "unit": UNIT,
+                         "h2d_bytes_per_step": BATCH * 4 * N_DOF, "d2h_bytes_per_step": BATCH * (28 + 24 * N_DOF),
+                         "steps": e2e_steps, "api": "drmb200_fk_jacobian_host (pinned host buffers in and out)",
+                         "timing": "host wall clock around the blocking calls (they return after the last D2H), max over ranks"}
+
+    if rank == 0:
+        result["clocks"] = sampler.summary()
+        if not args.no_cpu_baseline:
+            times = time_cpu_port(BATCH, 10.0, 200)
+            cores = os.cpu_count() or 1
+            v = BATCH * len(times) / sum(times)
+            result["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{len(times)} calls x {BATCH} configurations of the same workload through "
+                          f"oracle/drm_oracle.py (torch CPU port of the reference's per-link algorithm, fp32), "
+                          f"{cores} threads, {sum(times):.1f} s",
+            }
+        print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,28 @@
+#!/bin/bash
+# Run on the B200 box via:  gpurun --timeout 1500 -- 'bash scripts/gpu_checks.sh [quick]'
+# Parity tests, smoke, bench (both staging variants), ncu launch list and one --set full capture.
+set -u
+mkdir -p gpurun_out
+cd "${GRAFT_REPO_ROOT:-.}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
+nproc > gpurun_out/nproc.txt; lscpu | grep 'Model name' >> gpurun_out/nproc.txt
+
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log
+echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -5 | tee gpurun_out/smoke.log
+
+echo "== bench (TMA bulk staging)"; timeout 600 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/bench.json
+tail -3 gpurun_out/bench.err
+echo "== bench (cooperative staging)"; DRMB200_FK_VARIANT=0 timeout 300 python bench.py --no-cpu-baseline --no-e2e 2>> gpurun_out/bench.err | tee gpurun_out/bench_coop.json
+if [ "${1:-}" = "quick" ]; then exit 0; fi
+
+echo "== reference arm"; timeout 400 python bench.py --impl reference --steps 20 --warmup 3 2>> gpurun_out/bench.err | tee gpurun_out/bench_reference.json
+
+echo "== ncu launch list"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    python bench.py --steps 48 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_under_ncu.log 2>&1
+echo "== ncu --set full (fk_jacobian, batch 65536 and 2^22)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fk_jacobian -s 20 -c 3 -f -o gpurun_out/fk_small \
+    python bench.py --steps 48 --warmup 3 --no-cpu-baseline --no-e2e --no-large > gpurun_out/ncu_small.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:fk_jacobian -s 105 -c 2 -f -o gpurun_out/fk_large \
+    python bench.py --steps 48 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu_large.log 2>&1
+ls -la gpurun_out

@@ -1,0 +1,279 @@
+"""GPU: parity of the CUDA engine (called through the Python API -> ctypes -> C ABI) with
+
+  * the golden vectors produced by the reference itself (tests/golden/*.npz, every shipped URDF);
+  * the fp64 CPU oracle (oracle/drm_oracle.py) on seeded inputs at sizes it finishes in seconds;
+  * size-independent properties at BASELINE.json's full batch sizes.
+
+Tolerances: FK / Jacobian  allclose(rtol=1e-5, atol=1e-6) -- the reference's own atol
+(tests/test_kinematics_dynamics.py:265-274, 314-323) and north_star's 1e-5 relative;
+inverse dynamics atol=1e-5 (tests/test_kinematics_dynamics.py:373-377).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, canon_quat, load_golden, urdf_path
+import differentiable_robot_model_b200 as drm
+from differentiable_robot_model_b200 import engine
+from oracle import drm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def gpu_model(stem):
+    return drm.DifferentiableRobotModel(urdf_path(stem), stem, device=DEV)
+
+
+def cuda(a):
+    return torch.tensor(np.asarray(a), dtype=torch.float32, device=DEV)
+
+
+@pytest.fixture(params=[1, 0], ids=["tma_bulk", "coop_copy"])
+def fk_variant(request):
+    engine.set_option("fk_variant", request.param)
+    yield request.param
+    engine.set_option("fk_variant", 1)
+
+
+# ------------------------------------------------------------------------------------------------
+# golden vectors (reference outputs), every shipped URDF
+# ------------------------------------------------------------------------------------------------
+def test_fk_jacobian_matches_reference_golden(robot_stem, fk_variant):
+    g = load_golden(robot_stem)
+    m = gpu_model(robot_stem)
+    q = cuda(g["q"])
+    launches = engine.launch_count()
+    for link in g["fk_links"].tolist():
+        pos, quat = m.compute_forward_kinematics(q, link)
+        jl, ja = m.compute_endeffector_jacobian(q, link)
+        fpos, fquat, fjl, fja = m.compute_fk_and_jacobian(q, link)
+        assert_close(pos.cpu().numpy(), g[f"pos.{link}"], what=f"pos {link}")
+        assert_close(canon_quat(quat.cpu().numpy()), canon_quat(g[f"quat.{link}"]), what=f"quat {link}")
+        assert_close(jl.cpu().numpy(), g[f"jlin.{link}"], what=f"jlin {link}")
+        assert_close(ja.cpu().numpy(), g[f"jang.{link}"], what=f"jang {link}")
+        # the fused op is the same kernel with all outputs enabled: bit-identical
+        for a, b in ((pos, fpos), (quat, fquat), (jl, fjl), (ja, fja)):
+            assert torch.equal(a, b)
+        # raw sign convention of the quaternion (away from branch boundaries)
+        same = np.abs(quat.cpu().numpy() - g[f"quat.{link}"]).max(axis=1) < 1e-5
+        assert same.mean() >= 0.85
+    assert engine.launch_count() - launches == 3 * len(g["fk_links"])
+
+
+def test_inverse_dynamics_matches_reference_golden(robot_stem):
+    g = load_golden(robot_stem)
+    m = gpu_model(robot_stem)
+    q, qd, qdd = cuda(g["q"]), cuda(g["qd"]), cuda(g["qdd"])
+    for grav in (0, 1):
+        for damp in (0, 1):
+            tau = m.compute_inverse_dynamics(q, qd, qdd, include_gravity=bool(grav), use_damping=bool(damp))
+            assert_close(tau.cpu().numpy(), g[f"tau.g{grav}d{damp}"], rtol=1e-5, atol=1e-5, what=f"tau g{grav}d{damp}")
+    nle = m.compute_non_linear_effects(q, qd)
+    ref = m.compute_inverse_dynamics(q, qd, torch.zeros_like(q))
+    assert torch.equal(nle, ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# fp64 oracle on seeded batches (ragged sizes exercise partial tiles and the non-bulk tail path)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("batch", [1, 3, 255, 256, 257, 1001, 4099])
+def test_fk_jacobian_matches_oracle(batch, fk_variant):
+    for stem, link in (("iiwa7", "iiwa_link_ee"), ("allegro_hand_description_left", "link_15.0_tip"),
+                       ("iiwa7_allegro", "link_3.0_tip")):
+        robot = O.load_robot(urdf_path(stem), torch.float64)
+        q, _, _ = O.sample_inputs(robot, batch, seed=batch)
+        m = gpu_model(stem)
+        pos, quat, jl, ja = m.compute_fk_and_jacobian(q.to(DEV), link)
+        o_pos, o_quat = O.forward_kinematics(robot, q.double(), link)
+        o_jl, o_ja = O.jacobian(robot, q.double(), link)
+        assert_close(pos.cpu().numpy(), o_pos.numpy(), what=f"{stem} pos")
+        assert_close(canon_quat(quat.cpu().numpy()), canon_quat(o_quat.numpy()), what=f"{stem} quat")
+        assert_close(jl.cpu().numpy(), o_jl.numpy(), what=f"{stem} jlin")
+        assert_close(ja.cpu().numpy(), o_ja.numpy(), what=f"{stem} jang")
+
+
+@pytest.mark.parametrize("batch", [1, 5, 127, 128, 129, 1003])
+def test_inverse_dynamics_matches_oracle(batch):
+    for stem in ("panda_no_gripper", "iiwa7", "allegro_hand_description_left", "trifinger_edu", "jaco_clean",
+                 "iiwa7_allegro"):
+        robot = O.load_robot(urdf_path(stem), torch.float64)
+        q, qd, qdd = O.sample_inputs(robot, batch, seed=100 + batch)
+        m = gpu_model(stem)
+        tau = m.compute_inverse_dynamics(q.to(DEV), qd.to(DEV), qdd.to(DEV))
+        o_tau = O.inverse_dynamics(robot, q.double(), qd.double(), qdd.double())
+        scale = float(o_tau.abs().max())
+        assert_close(tau.cpu().numpy(), o_tau.numpy(), rtol=1e-5, atol=max(1e-5, 2e-6 * scale), what=f"{stem} tau")
+
+
+# ------------------------------------------------------------------------------------------------
+# edge cases
+# ------------------------------------------------------------------------------------------------
+def test_empty_batch_and_1d_inputs(fk_variant):
+    m = gpu_model("iiwa7")
+    pos, quat, jl, ja = m.compute_fk_and_jacobian(torch.zeros(0, 7, device=DEV), "iiwa_link_ee")
+    assert pos.shape == (0, 3) and quat.shape == (0, 4) and jl.shape == (0, 3, 7) and ja.shape == (0, 3, 7)
+    tau = m.compute_inverse_dynamics(*(torch.zeros(0, 7, device=DEV),) * 3)
+    assert tau.shape == (0, 7)
+    # 1-D input -> outputs with the batch dimension removed (robot_model.py:58-62)
+    q1 = torch.linspace(-1, 1, 7, device=DEV)
+    pos, quat = m.compute_forward_kinematics(q1, "iiwa_link_ee")
+    jl, ja = m.compute_endeffector_jacobian(q1, "iiwa_link_ee")
+    tau = m.compute_inverse_dynamics(q1, q1, q1)
+    assert pos.shape == (3,) and quat.shape == (4,) and jl.shape == (3, 7) and ja.shape == (3, 7) and tau.shape == (7,)
+    pos2, _ = m.compute_forward_kinematics(q1[None], "iiwa_link_ee")
+    assert torch.equal(pos, pos2[0])
+    # zero pose known answer: 0.15+0.19+0.21+0.19+0.21+0.19+0.081+0.045 = 1.266
+    pos0, quat0 = m.compute_forward_kinematics(torch.zeros(7, device=DEV), "iiwa_link_ee")
+    assert_close(pos0.cpu().numpy(), [0, 0, 1.266], what="zero pose")
+    assert_close(quat0.cpu().numpy(), [0, 0, 0, 1], what="zero quat")
+
+
+def test_root_link_and_mid_chain_links():
+    m = gpu_model("iiwa7")
+    q = torch.rand(33, 7, device=DEV)
+    pos, quat, jl, ja = m.compute_fk_and_jacobian(q, "iiwa_link_0")         # the root: identity, zero Jacobian
+    assert torch.equal(pos, torch.zeros_like(pos)) and torch.equal(jl, torch.zeros_like(jl))
+    assert torch.equal(quat, torch.tensor([0.0, 0, 0, 1], device=DEV).expand(33, 4))
+    _, _, jl, ja = m.compute_fk_and_jacobian(q, "iiwa_link_3")              # columns 3..6 are off the path
+    assert torch.equal(jl[:, :, 3:], torch.zeros_like(jl[:, :, 3:])) and torch.equal(ja[:, :, 3:], torch.zeros_like(ja[:, :, 3:]))
+    assert float(ja[:, :, :3].abs().sum()) > 0
+
+
+def test_unaligned_and_noncontiguous_inputs(fk_variant):
+    m = gpu_model("iiwa7")
+    base = torch.rand(1030, 7, device=DEV) * 4 - 2
+    want = m.compute_fk_and_jacobian(base[1:1025].clone(), "iiwa_link_ee")
+    got = m.compute_fk_and_jacobian(base[1:1025], "iiwa_link_ee")          # data_ptr offset 28 B: not 16-B aligned
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    wide = torch.rand(513, 14, device=DEV)
+    got = m.compute_fk_and_jacobian(wide[:, ::2], "iiwa_link_ee")           # non-contiguous view
+    want = m.compute_fk_and_jacobian(wide[:, ::2].contiguous(), "iiwa_link_ee")
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    t1 = m.compute_inverse_dynamics(base[1:1025], base[2:1026], base[3:1027])
+    t2 = m.compute_inverse_dynamics(base[1:1025].clone(), base[2:1026].clone(), base[3:1027].clone())
+    assert torch.equal(t1, t2)
+
+
+def test_large_joint_angles_use_accurate_range_reduction():
+    m = gpu_model("iiwa7")
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float64)
+    q = (torch.rand(512, 7, dtype=torch.float64) * 2 - 1) * 200.0          # far outside the joint limits
+    q32 = q.to(torch.float32)
+    pos, quat, jl, ja = m.compute_fk_and_jacobian(q32.to(DEV), "iiwa_link_ee")
+    o_pos, _ = O.forward_kinematics(robot, q32.double(), "iiwa_link_ee")
+    o_jl, o_ja = O.jacobian(robot, q32.double(), "iiwa_link_ee")
+    assert_close(pos.cpu().numpy(), o_pos.numpy(), atol=3e-6, what="pos, |q| <= 200 rad")
+    assert_close(jl.cpu().numpy(), o_jl.numpy(), atol=3e-6, what="jlin, |q| <= 200 rad")
+    huge = torch.full((4, 7), 3.0e6, device=DEV)                            # slow-path (Payne-Hanek) branch
+    pos, _ = m.compute_forward_kinematics(huge, "iiwa_link_ee")
+    o_pos, _ = O.forward_kinematics(robot, huge.cpu().double(), "iiwa_link_ee")
+    assert_close(pos.cpu().numpy(), o_pos.numpy(), atol=3e-6, what="pos, q = 3e6 rad")
+
+
+def test_device_and_argument_errors():
+    m = gpu_model("iiwa7")
+    with pytest.raises(AssertionError):                       # CPU tensor into a CUDA model (robot_model.py:38-40)
+        m.compute_forward_kinematics(torch.zeros(3, 7), "iiwa_link_ee")
+    with pytest.raises(AssertionError):
+        m.compute_inverse_dynamics(torch.zeros(3, 7, device=DEV), torch.zeros(3, 6, device=DEV), torch.zeros(3, 7, device=DEV))
+    with pytest.raises(KeyError):
+        m.compute_endeffector_jacobian(torch.zeros(3, 7, device=DEV), "nope")
+    with pytest.raises(RuntimeError, match="fp32-only"):
+        m.compute_forward_kinematics(torch.zeros(3, 7, device=DEV, dtype=torch.float64), "iiwa_link_ee")
+    # C ABI error codes surface as RuntimeError with the library's message
+    with pytest.raises(RuntimeError, match="ee_link"):
+        engine.fk_jacobian_raw(m._topology, 77, m._link_table(), torch.zeros(3, 7, device=DEV))
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at the BASELINE.json batch sizes
+# ------------------------------------------------------------------------------------------------
+def test_full_size_fk_jacobian_properties():
+    """Config 2: Kuka iiwa FK + Jacobian, batch 65 536."""
+    m = gpu_model("iiwa7")
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float64)
+    B = 65536
+    q, _, _ = O.sample_inputs(robot, B, seed=7)
+    q = q.to(DEV)
+    pos, quat, jl, ja = m.compute_fk_and_jacobian(q, "iiwa_link_ee")
+    assert torch.isfinite(pos).all() and torch.isfinite(jl).all()
+    # unit quaternions, unit joint axes
+    assert float((quat.norm(dim=1) - 1).abs().max()) < 2e-6
+    assert float((ja.norm(dim=1) - 1).abs().max()) < 2e-6
+    # 2 pi periodicity of every revolute joint
+    pos2, quat2, jl2, ja2 = m.compute_fk_and_jacobian(q + 2 * np.pi, "iiwa_link_ee")
+    assert float((pos - pos2).abs().max()) < 5e-6 and float((jl - jl2).abs().max()) < 5e-6
+    # tiling independence: any sub-batch gives bit-identical rows (a checksum of checksums)
+    idx = torch.randperm(B, device=DEV)[:10007]
+    sub = m.compute_fk_and_jacobian(q[idx], "iiwa_link_ee")
+    for full, part in zip((pos, quat, jl, ja), sub):
+        assert torch.equal(full[idx], part)
+    # the linear Jacobian is the derivative of the position: central differences along a random direction
+    d = torch.randn(B, 7, device=DEV)
+    h = 1e-3
+    pp, _ = m.compute_forward_kinematics(q + h * d, "iiwa_link_ee")
+    pm, _ = m.compute_forward_kinematics(q - h * d, "iiwa_link_ee")
+    fd = (pp - pm) / (2 * h)
+    an = torch.einsum("bij,bj->bi", jl, d)
+    assert float((fd - an).abs().max()) < 2e-3 * float(an.abs().max())
+    # spot-check 2048 rows against the fp64 oracle
+    rows = idx[:2048].cpu()
+    o_pos, o_quat = O.forward_kinematics(robot, q.cpu().double()[rows], "iiwa_link_ee")
+    o_jl, o_ja = O.jacobian(robot, q.cpu().double()[rows], "iiwa_link_ee")
+    assert_close(pos.cpu().numpy()[rows], o_pos.numpy(), what="pos")
+    assert_close(canon_quat(quat.cpu().numpy()[rows]), canon_quat(o_quat.numpy()), what="quat")
+    assert_close(jl.cpu().numpy()[rows], o_jl.numpy(), what="jlin")
+    assert_close(ja.cpu().numpy()[rows], o_ja.numpy(), what="jang")
+
+
+def test_full_size_inverse_dynamics_properties():
+    """Config 3: Franka Panda RNEA, batch 65 536."""
+    m = gpu_model("panda_no_gripper")
+    robot = O.load_robot(urdf_path("panda_no_gripper"), torch.float64)
+    B = 65536
+    q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, B, seed=11))
+    tau = m.compute_inverse_dynamics(q, qd, qdd)
+    assert torch.isfinite(tau).all()
+    # tau is affine in qdd: tau(a) + tau(b) - tau(0) == tau(a + b)
+    a, b = torch.randn_like(qdd), torch.randn_like(qdd)
+    t = lambda x: m.compute_inverse_dynamics(q, qd, x)  # noqa: E731
+    lhs, rhs = t(a) + t(b) - t(torch.zeros_like(a)), t(a + b)
+    assert float((lhs - rhs).abs().max()) < 2e-4 * max(1.0, float(rhs.abs().max()))
+    # damping enters as damping * qd; gravity term is velocity independent
+    d_on = m.compute_inverse_dynamics(q, qd, qdd, use_damping=True)
+    d_off = m.compute_inverse_dynamics(q, qd, qdd, use_damping=False)
+    damp = torch.stack([b_.get_joint_damping_const().reshape(()) for b_ in (m._bodies[i] for i in m._controlled_joints)])
+    assert float((d_on - d_off - damp * qd).abs().max()) < 1e-5
+    # the mass matrix extracted column by column is symmetric positive definite
+    z = torch.zeros_like(q[:4096])
+    g_ = m.compute_inverse_dynamics(q[:4096], z, z)
+    cols = []
+    for j in range(7):
+        e = z.clone(); e[:, j] = 1.0
+        cols.append(m.compute_inverse_dynamics(q[:4096], z, e) - g_)
+    H = torch.stack(cols, dim=2)
+    assert float((H - H.transpose(1, 2)).abs().max()) < 1e-4
+    assert float(torch.linalg.eigvalsh(H.double().cpu()).min()) > 0
+    # tiling independence + oracle spot check
+    idx = torch.randperm(B, device=DEV)[:5003]
+    assert torch.equal(tau[idx], m.compute_inverse_dynamics(q[idx], qd[idx], qdd[idx]))
+    rows = idx[:1024].cpu()
+    o_tau = O.inverse_dynamics(robot, q.cpu().double()[rows], qd.cpu().double()[rows], qdd.cpu().double()[rows])
+    assert_close(tau.cpu().numpy()[rows], o_tau.numpy(), rtol=1e-5, atol=max(1e-5, 2e-6 * float(o_tau.abs().max())), what="tau")
+
+
+def test_host_buffer_entry_point_matches_device_path():
+    m = gpu_model("iiwa7")
+    B = 150001                                               # several pipeline chunks + a ragged tail
+    q_host = (torch.rand(B, 7) * 4 - 2).pin_memory()
+    outs = [torch.empty(B, 3).pin_memory(), torch.empty(B, 4).pin_memory(), torch.empty(B, 3, 7).pin_memory(),
+            torch.empty(B, 3, 7).pin_memory()]
+    engine.fk_jacobian_host(m._topology, m._name_to_idx_map["iiwa_link_ee"], 0, m._link_table(), q_host, *outs)
+    want = m.compute_fk_and_jacobian(q_host.to(DEV), "iiwa_link_ee")
+    for got, w in zip(outs, want):
+        assert torch.equal(got, w.cpu())
