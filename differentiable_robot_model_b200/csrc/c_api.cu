@@ -14,7 +14,7 @@ namespace drm {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-static std::atomic<int> g_fk_variant{-1};
+static std::atomic<int> g_options[2] = {{-1}, {-1}};   // 0: fk_variant, 1: fk_tile
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -24,14 +24,15 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-// FK staging variant: 1 = TMA bulk copies (default), 0 = cooperative float4 copies.
-// Overridable for A/B measurements with DRMB200_FK_VARIANT or drmb200_set_option("fk_variant", v).
-int fk_variant() {
-    int v = g_fk_variant.load(std::memory_order_relaxed);
+// Tuning knobs for A/B measurements, overridable with the environment or drmb200_set_option():
+//   0 "fk_variant" (DRMB200_FK_VARIANT): 1 = TMA bulk-copy staging (default), 0 = cooperative float4 copies
+//   1 "fk_tile"    (DRMB200_FK_TILE):    configurations per CTA, 64 / 128 / 256; 0 = pick by batch size
+int get_option(int which) {
+    int v = g_options[which].load(std::memory_order_relaxed);
     if (v < 0) {
-        const char* e = getenv("DRMB200_FK_VARIANT");
-        v = e ? atoi(e) : 1;
-        g_fk_variant.store(v, std::memory_order_relaxed);
+        const char* e = getenv(which == 0 ? "DRMB200_FK_VARIANT" : "DRMB200_FK_TILE");
+        v = e ? atoi(e) : (which == 0 ? 1 : 0);
+        g_options[which].store(v, std::memory_order_relaxed);
     }
     return v;
 }
@@ -150,7 +151,8 @@ int64_t drmb200_launch_count(void) { return drm::g_launches.load(); }
 
 // not part of the reference-facing surface: A/B switch used by bench.py and the tests
 int drmb200_set_option(const char* name, int value) {
-    if (name != nullptr && std::string(name) == "fk_variant") { drm::g_fk_variant.store(value); return DRMB200_OK; }
+    if (name != nullptr && std::string(name) == "fk_variant") { drm::g_options[0].store(value); return DRMB200_OK; }
+    if (name != nullptr && std::string(name) == "fk_tile") { drm::g_options[1].store(value); return DRMB200_OK; }
     drm::set_error("unknown option");
     return DRMB200_EINVAL;
 }

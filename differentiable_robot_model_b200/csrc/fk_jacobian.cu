@@ -10,25 +10,25 @@
 // Mapping: one thread per joint configuration, TILE configurations per CTA.
 //   * The outputs of a link depend only on its ancestors, so the kernel walks just the root->ee
 //     chain (the "path program", a by-value kernel parameter living in the constant bank).
+//   * Canonical joint frames (drm_common.cuh): the link-table rows are staged into shared memory
+//     through a signed permutation so that every movable joint is a +z rotation.  The inner loop
+//     has no axis dispatch: R <- (R F~) Rz(q), joint axis z_i = third column, 39 FMA + sincos.
 //   * q tile in / (pos, quat, J_lin, J_ang) tiles out are staged through shared memory in the
-//     SAME row-major layout as global memory, so each tile moves as one contiguous block:
-//       variant 1: TMA 1-D bulk copies (cp.async.bulk, mbarrier completion) issued by one thread;
-//       variant 0: cooperative float4 copies (also the fallback for ragged tails / unaligned bases).
-//     Per-thread smem rows have odd strides for odd n_dofs (7 -> 7, 21 floats), hence no bank conflicts.
+//     SAME row-major layout as global memory, so each tile moves as one contiguous block with
+//     TMA 1-D bulk copies (cp.async.bulk + mbarrier; SASS UBLKCP) issued by one thread.  Ragged
+//     tails / unaligned bases fall back to cooperative float4 copies.  n_dofs is a template
+//     parameter for the common sizes so every smem access is base + immediate; per-thread rows have
+//     odd strides for odd n_dofs (7 -> 7, 21 floats), hence no bank conflicts.
 //   * The world rotation R (9) and position p (3) stay in registers along the chain.  Jacobian
 //     columns need p_ee, known only at the end of the walk, so during the walk each path joint
 //     stores z_i (= its J_ang column, final) and z_i x p_i in the J_lin slot of the smem tile; a
 //     short second pass rewrites J_lin = z_i x p_ee - z_i x p_i.
-//   * The float link table (F, r per link; differentiable, device memory) is staged once per CTA
-//     into shared memory and read with warp-broadcast LDS.128.
 //
 // Algorithmic HBM bytes per configuration: 4n (q) + 12 (pos) + 16 (quat) + 24n (J) = 28n + 28
 // (224 B for the 7-DoF Kuka iiwa) -- SURVEY.md section 8(d).
 #include "drm_common.cuh"
 
 namespace drm {
-
-constexpr int FK_TILE = 256;       // configurations per CTA == threads per CTA
 
 struct FkArgs {
     const float* __restrict__ table;     // [n_links, 28]
@@ -38,52 +38,34 @@ struct FkArgs {
     float* __restrict__ jlin;            // [B, 3, n] or null
     float* __restrict__ jang;            // [B, 3, n] or null
     int64_t batch;
-    int32_t bulk_ok;                     // all base pointers 16-byte aligned
+    int32_t aligned;                     // all base pointers 16-byte aligned
+    int32_t use_bulk;                    // staging variant: 1 TMA bulk copies, 0 cooperative copies
 };
 
 // shared-memory carve-up (floats), natural global layout per region
 struct FkSmemLayout {
     int q, pos, quat, jlin, jang, table, total_floats;
-    __host__ __device__ FkSmemLayout(int n, int path_len, bool with_jac) {
+    __host__ __device__ FkSmemLayout(int tile, int n, int path_len, bool with_jac) {
         int o = 0;
-        quat = o; o += FK_TILE * 4;            // 16-byte aligned rows first
-        q = o;    o += FK_TILE * n;
-        pos = o;  o += FK_TILE * 3;
-        jlin = o; o += with_jac ? FK_TILE * 3 * n : 0;
-        jang = o; o += with_jac ? FK_TILE * 3 * n : 0;
+        quat = o; o += tile * 4;               // 16-byte aligned rows first
+        q = o;    o += tile * n;
+        pos = o;  o += tile * 3;
+        jlin = o; o += with_jac ? tile * 3 * n : 0;
+        jang = o; o += with_jac ? tile * 3 * n : 0;
         table = o; o += path_len * 12;
         total_floats = o;
     }
 };
 
-// cooperative linear copy global -> shared / shared -> global (layout identical on both sides)
-__device__ __forceinline__ void coop_copy_in(float* s, const float* g, int nfloats, bool vec_ok) {
-    if (vec_ok && (nfloats & 3) == 0) {
-        const float4* g4 = reinterpret_cast<const float4*>(g);
-        float4* s4 = reinterpret_cast<float4*>(s);
-        for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) s4[i] = __ldg(g4 + i);
-    } else {
-        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) s[i] = __ldg(g + i);
-    }
-}
-__device__ __forceinline__ void coop_copy_out(float* g, const float* s, int nfloats, bool vec_ok) {
-    if (vec_ok && (nfloats & 3) == 0) {
-        float4* g4 = reinterpret_cast<float4*>(g);
-        const float4* s4 = reinterpret_cast<const float4*>(s);
-        for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) g4[i] = s4[i];
-    } else {
-        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) g[i] = s[i];
-    }
-}
-
-template <bool WITH_JAC, bool USE_BULK>
-__global__ void __launch_bounds__(FK_TILE, 3)
+template <int NDOF, int TILE, bool WITH_JAC>
+__global__ void __launch_bounds__(TILE)
 fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t mbar;
 
-    const int n = prog.n_dofs;
-    const FkSmemLayout L(n, prog.len, WITH_JAC);
+    const int n = NDOF > 0 ? NDOF : prog.n_dofs;
+    const int len = prog.len;
+    const FkSmemLayout L(TILE, n, len, WITH_JAC);
     float* s_q = smem + L.q;
     float* s_pos = smem + L.pos;
     float* s_quat = smem + L.quat;
@@ -92,11 +74,11 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
     float* s_tab = smem + L.table;
 
     const int tid = threadIdx.x;
-    const int64_t tile_start = (int64_t)blockIdx.x * FK_TILE;
-    const int valid = (int)min((int64_t)FK_TILE, args.batch - tile_start);
+    const int64_t tile_start = (int64_t)blockIdx.x * TILE;
+    const int valid = (int)min((int64_t)TILE, args.batch - tile_start);
     // bulk copies need 16-byte multiples: rows are 4n / 12 / 16 / 12n bytes -> valid % 4 == 0
-    const bool bulk = USE_BULK && args.bulk_ok && ((valid & 3) == 0);
-    const bool vec_ok = args.bulk_ok;   // base pointers 16-byte aligned; tile offsets always are
+    const bool bulk = args.use_bulk && args.aligned && ((valid & 3) == 0);
+    const bool vec_ok = args.aligned;   // base pointers 16-byte aligned; tile offsets always are
 
     // ---- stage inputs --------------------------------------------------------------------------
     if (bulk) {
@@ -108,17 +90,19 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
             bulk_g2s(s_q, args.q + tile_start * n, bytes, &mbar);
         }
     } else {
-        coop_copy_in(s_q, args.q + tile_start * n, valid * n, vec_ok);
+        coop_copy(s_q, args.q + tile_start * n, valid * n, vec_ok);
     }
-    // link-table rows of the path (F, r) -> smem
-    for (int i = tid; i < prog.len * 12; i += FK_TILE) {
-        int k = i / 12, e = i - k * 12;
-        s_tab[i] = __ldg(args.table + (int)prog.link[k] * DRMB200_TABLE_STRIDE + e);
+    // canonical (F~, r~) rows of the path links -> smem
+    for (int i = tid; i < len * 12; i += TILE) {
+        const int k = i / 12, e = i - k * 12;
+        int src;
+        const float sg = canon_map(e, prog.paxis[k], prog.axis[k], src);
+        s_tab[i] = sg * __ldg(args.table + (int)prog.link[k] * DRMB200_TABLE_STRIDE + src);
     }
     if (WITH_JAC && !prog.full_cover) {      // columns of joints off the path stay zero
-        float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float4* j4 = reinterpret_cast<float4*>(s_jlin);      // jlin and jang are adjacent
-        for (int i = tid; i < (FK_TILE * 6 * n) / 4; i += FK_TILE) j4[i] = z4;
+        for (int i = tid; i < (TILE * 6 * n) / 4; i += TILE) j4[i] = z4;
     }
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
@@ -131,43 +115,33 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
         float* jl = s_jlin + tid * 3 * n;
         float* ja = s_jang + tid * 3 * n;
 
-        for (int k = 0; k < prog.len; ++k) {
-            const float4* t4 = reinterpret_cast<const float4*>(s_tab + k * 12);
-            const float4 f0 = t4[0], f1 = t4[1], f2 = t4[2];
-            M3 F; F.a00 = f0.x; F.a01 = f0.y; F.a02 = f0.z; F.a10 = f0.w; F.a11 = f1.x; F.a12 = f1.y;
-            F.a20 = f1.z; F.a21 = f1.w; F.a22 = f2.x;
-            const V3 r = v3(f2.y, f2.z, f2.w);
-
+        for (int k = 0; k < len; ++k) {
+            M3 F; V3 r;
+            load_Fr(s_tab + k * 12, F, r);
             p = mul_add(R, r, p);            // p_i = R_parent r_i + p_parent
             R = mul(R, F);                   // R_parent F_i
-            const int ax = prog.axis[k];
-            if (ax != 0) {
-                const int a = (ax > 0 ? ax : -ax) - 1;
-                float th = qrow[prog.dof[k]];
-                if (ax < 0) th = -th;        // angle = sign(axis) * q   (rigid_body.py:149-154)
+            const int c = prog.dof[k];
+            if (c >= 0) {
                 float sn, cs;
-                sincos_pi2(th, sn, cs);
+                sincos_pi2(qrow[c], sn, cs);
                 if (WITH_JAC) {
-                    // z_i = R_i s_i: the joint rotation leaves its own axis column unchanged
-                    V3 z = col(R, a);
-                    if (ax < 0) z = v3(-z.x, -z.y, -z.z);
+                    const V3 z = col2(R);    // joint axis in the world frame (unchanged by Rz)
                     const V3 m = cross(z, p);
-                    const int c = prog.dof[k];
                     ja[c] = z.x; ja[n + c] = z.y; ja[2 * n + c] = z.z;
                     jl[c] = m.x; jl[n + c] = m.y; jl[2 * n + c] = m.z;
                 }
-                apply_joint_rotation(R, a, cs, sn);
+                rotate_z(R, cs, sn);
             }
         }
 
         if (args.pos != nullptr) { s_pos[tid * 3 + 0] = p.x; s_pos[tid * 3 + 1] = p.y; s_pos[tid * 3 + 2] = p.z; }
-        if (args.quat != nullptr) reinterpret_cast<float4*>(s_quat)[tid] = quat_xyzw(R);
+        if (args.quat != nullptr) reinterpret_cast<float4*>(s_quat)[tid] = quat_xyzw(unpermute_cols(R, prog.ee_axis));
 
         if (WITH_JAC) {
             // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
-            for (int k = 0; k < prog.len; ++k) {
-                if (prog.axis[k] == 0) continue;
+            for (int k = 0; k < len; ++k) {
                 const int c = prog.dof[k];
+                if (c < 0) continue;
                 const V3 z = v3(ja[c], ja[n + c], ja[2 * n + c]);
                 const V3 m = v3(jl[c], jl[n + c], jl[2 * n + c]);
                 const V3 j = cross_add(z, p, v3(-m.x, -m.y, -m.z));
@@ -192,11 +166,11 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
         }
     } else {
         __syncthreads();
-        if (args.pos != nullptr) coop_copy_out(args.pos + tile_start * 3, s_pos, valid * 3, vec_ok);
-        if (args.quat != nullptr) coop_copy_out(args.quat + tile_start * 4, s_quat, valid * 4, vec_ok);
+        if (args.pos != nullptr) coop_copy(args.pos + tile_start * 3, s_pos, valid * 3, vec_ok);
+        if (args.quat != nullptr) coop_copy(args.quat + tile_start * 4, s_quat, valid * 4, vec_ok);
         if (WITH_JAC) {
-            coop_copy_out(args.jlin + tile_start * 3 * n, s_jlin, valid * 3 * n, vec_ok);
-            coop_copy_out(args.jang + tile_start * 3 * n, s_jang, valid * 3 * n, vec_ok);
+            coop_copy(args.jlin + tile_start * 3 * n, s_jlin, valid * 3 * n, vec_ok);
+            coop_copy(args.jang + tile_start * 3 * n, s_jang, valid * 3 * n, vec_ok);
         }
     }
 }
@@ -210,6 +184,7 @@ int build_path_program(const drmb200_topology_t* topo, int32_t ee_link, PathProg
         set_error("n_links=%d outside [1, %d]", topo->n_links, DRMB200_MAX_LINKS);
         return DRMB200_ELIMIT;
     }
+    if (topo->n_dofs < 0 || topo->n_dofs > topo->n_links) { set_error("n_dofs=%d inconsistent", topo->n_dofs); return DRMB200_EINVAL; }
     if (ee_link < 0 || ee_link >= topo->n_links) {
         set_error("ee_link=%d outside [0, %d)", ee_link, topo->n_links);
         return DRMB200_EINVAL;
@@ -225,29 +200,34 @@ int build_path_program(const drmb200_topology_t* topo, int32_t ee_link, PathProg
     }
     prog->len = len;
     prog->n_dofs = topo->n_dofs;
+    prog->ee_axis = 0;
     int covered = 0;
     for (int k = 0; k < len; ++k) {
-        int l = chain[len - 1 - k];
+        const int l = chain[len - 1 - k];
+        const int ax = topo->axis[l];
         prog->link[k] = (int8_t)l;
-        prog->axis[k] = topo->axis[l];
-        prog->dof[k] = topo->dof[l];
-        if (topo->axis[l] != 0) {
-            if (topo->dof[l] < 0 || topo->dof[l] >= topo->n_dofs || abs((int)topo->axis[l]) > 3) {
-                set_error("link %d: bad dof/axis (%d, %d)", l, (int)topo->dof[l], (int)topo->axis[l]);
+        prog->axis[k] = (int8_t)ax;
+        prog->paxis[k] = (k == 0) ? 0 : prog->axis[k - 1];
+        prog->dof[k] = (ax != 0) ? topo->dof[l] : (int8_t)-1;
+        if (ax != 0) {
+            if (topo->dof[l] < 0 || topo->dof[l] >= topo->n_dofs || ax > 3 || ax < -3) {
+                set_error("link %d: bad dof/axis (%d, %d)", l, (int)topo->dof[l], ax);
                 return DRMB200_EINVAL;
             }
             ++covered;
         }
+        if (k == len - 1) prog->ee_axis = ax;
     }
     prog->full_cover = (covered == topo->n_dofs) ? 1 : 0;
     return DRMB200_OK;
 }
 
-template <bool WITH_JAC, bool USE_BULK>
+template <int NDOF, int TILE, bool WITH_JAC>
 static int launch_fk(const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
-    const FkSmemLayout L(prog.n_dofs, prog.len, WITH_JAC);
+    const FkSmemLayout L(TILE, prog.n_dofs, prog.len, WITH_JAC);
     const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
-    auto kern = fk_jacobian_kernel<WITH_JAC, USE_BULK>;
+    if (smem_bytes > 227 * 1024) { set_error("fk kernel needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
+    auto kern = fk_jacobian_kernel<NDOF, TILE, WITH_JAC>;
     static size_t configured_by_dev[64] = {0};     // per instantiation, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -257,12 +237,24 @@ static int launch_fk(const PathProgram& prog, const FkArgs& args, cudaStream_t s
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
         configured = smem_bytes;
     }
-    const int64_t tiles = (args.batch + FK_TILE - 1) / FK_TILE;
-    kern<<<(unsigned)tiles, FK_TILE, smem_bytes, stream>>>(prog, args);
+    const int64_t tiles = (args.batch + TILE - 1) / TILE;
+    if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
+    kern<<<(unsigned)tiles, TILE, smem_bytes, stream>>>(prog, args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("fk_jacobian launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
     return DRMB200_OK;
+}
+
+template <int NDOF, int TILE>
+static int launch_fk_j(bool with_jac, const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
+    return with_jac ? launch_fk<NDOF, TILE, true>(prog, args, stream) : launch_fk<NDOF, TILE, false>(prog, args, stream);
+}
+template <int NDOF>
+static int launch_fk_t(int tile, bool with_jac, const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
+    if (tile == 64) return launch_fk_j<NDOF, 64>(with_jac, prog, args, stream);
+    if (tile == 256) return launch_fk_j<NDOF, 256>(with_jac, prog, args, stream);
+    return launch_fk_j<NDOF, 128>(with_jac, prog, args, stream);
 }
 
 int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const float* table, const float* q,
@@ -275,18 +267,28 @@ int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const fl
     if (batch == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr) { set_error("table / q is null"); return DRMB200_EINVAL; }
     if (pos == nullptr && quat == nullptr && jlin == nullptr) return DRMB200_OK;
-    if ((batch + FK_TILE - 1) / FK_TILE > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
 
     FkArgs args;
     args.table = table; args.q = q; args.pos = pos; args.quat = quat; args.jlin = jlin; args.jang = jang;
     args.batch = batch;
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    args.bulk_ok = (al16(q) && al16(pos) && al16(quat) && al16(jlin) && al16(jang)) ? 1 : 0;
+    args.aligned = (al16(q) && al16(pos) && al16(quat) && al16(jlin) && al16(jang)) ? 1 : 0;
+    args.use_bulk = get_option(0) != 0;
 
+    // Tile size: small tiles give more CTAs (better SM fill for small batches and more resident warps
+    // per SM, since shared memory -- 32 n + 28 bytes per configuration -- is the occupancy limiter).
+    int tile = get_option(1);
+    if (tile != 64 && tile != 128 && tile != 256) tile = (batch <= 148 * 1024) ? 64 : 128;
     const bool with_jac = jlin != nullptr;
-    const bool use_bulk = fk_variant() != 0;
-    if (with_jac) return use_bulk ? launch_fk<true, true>(prog, args, stream) : launch_fk<true, false>(prog, args, stream);
-    return use_bulk ? launch_fk<false, true>(prog, args, stream) : launch_fk<false, false>(prog, args, stream);
+    switch (prog.n_dofs) {
+        case 2: return launch_fk_t<2>(tile, with_jac, prog, args, stream);
+        case 7: return launch_fk_t<7>(tile, with_jac, prog, args, stream);
+        case 9: return launch_fk_t<9>(tile, with_jac, prog, args, stream);
+        case 12: return launch_fk_t<12>(tile, with_jac, prog, args, stream);
+        case 16: return launch_fk_t<16>(tile, with_jac, prog, args, stream);
+        case 23: return launch_fk_t<23>(tile, with_jac, prog, args, stream);
+        default: return launch_fk_t<0>(tile, with_jac, prog, args, stream);
+    }
 }
 
 }  // namespace drm

@@ -6,14 +6,16 @@
 // leaves->root, spatial_vector_algebra.py:204-236, 281-291, 321-338), the axis projection
 // (robot_model.py:353-365) and the damping term (robot_model.py:368-373).
 //
-// Closed form (verified against the reference), link i, parent p,
-// M = F_i Q_i(q), r = trans_i, s = signed joint axis, wJ = s qd:
-//   w_i  = M^T w_p + wJ                 v_i = M^T (v_p - r x w_p)
-//   al_i = M^T al_p + s qdd + w_i x wJ  a_i = M^T (a_p - r x al_p) + v_i x wJ      (a_0 = (0,0,9.81))
+// Closed form (verified against the reference), link i, parent p, in the canonical
+// joint frames of drm_common.cuh (every joint axis is e_z, joint rate (0,0,qd)):
+//   M = F~ Rz(q),  E = M^T,  r = r~
+//   w_i  = E w_p + (0,0,qd)                 v_i = E (v_p + w_p x r)
+//   al_i = E al_p + (0,0,qdd) + w_i x (0,0,qd)
+//   a_i  = E (a_p + al_p x r) + v_i x (0,0,qd)                        (a_0 = (0,0,9.81))
 //   h(W,V) = ( m V - mc x W ,  I_o W + mc x V )
 //   f_i  = h_lin(al,a) + w x h_lin(w,v)
 //   n_i  = h_ang(al,a) + w x h_ang(w,v) + v x h_lin(w,v)
-//   f_p += M f_i ;  n_p += r x (M f_i) + M n_i ;  tau_k = s . n_i + d_i qd_k
+//   f_p += M f_i ;  n_p += r x (M f_i) + M n_i ;  tau_k = n_i.z + d_i qd_k
 //
 // Mapping: one thread per configuration (RNEA_TILE per CTA).  The motion state (w, v, al, a) of the
 // current link lives in registers; only branch points of the tree spill it to shared-memory slots
@@ -40,7 +42,7 @@ struct RneaArgs {
     float* __restrict__ tau;
     int64_t batch;
     uint32_t flags;
-    int32_t bulk_ok;
+    int32_t aligned;
 };
 
 struct RneaSmemLayout {
@@ -58,34 +60,15 @@ struct RneaSmemLayout {
     }
 };
 
-struct LinkConsts {   // one table row, read by warp-broadcast LDS.128
-    M3 F; V3 r; M3 Io; V3 mc; float m, d;
-};
-__device__ __forceinline__ LinkConsts load_link(const float* row) {
-    const float4* t = reinterpret_cast<const float4*>(row);
-    const float4 a = t[0], b = t[1], c = t[2], d = t[3], e = t[4], f = t[5], g = t[6];
-    LinkConsts L;
-    L.F.a00 = a.x; L.F.a01 = a.y; L.F.a02 = a.z; L.F.a10 = a.w; L.F.a11 = b.x; L.F.a12 = b.y;
-    L.F.a20 = b.z; L.F.a21 = b.w; L.F.a22 = c.x;
-    L.r = v3(c.y, c.z, c.w);
-    L.Io.a00 = d.x; L.Io.a01 = d.y; L.Io.a02 = d.z; L.Io.a10 = d.w; L.Io.a11 = e.x; L.Io.a12 = e.y;
-    L.Io.a20 = e.z; L.Io.a21 = e.w; L.Io.a22 = f.x;
-    L.mc = v3(f.y, f.z, f.w);
-    L.m = g.x; L.d = g.y;
-    return L;
-}
-__device__ __forceinline__ V3 axis_vec(int a, float w) {    // w * e_a, a uniform
-    return v3(a == 0 ? w : 0.f, a == 1 ? w : 0.f, a == 2 ? w : 0.f);
-}
-__device__ __forceinline__ float comp(V3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
-
-__device__ __forceinline__ void coop_copy(float* dst, const float* src, int nfloats, bool vec_ok) {
-    if (vec_ok && (nfloats & 3) == 0) {
-        const float4* s4 = reinterpret_cast<const float4*>(src);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) d4[i] = s4[i];
-    } else {
-        for (int i = threadIdx.x; i < nfloats; i += blockDim.x) dst[i] = src[i];
+// stage the whole link table in canonical form (tree version: the parent's axis comes from prog)
+__device__ __forceinline__ void stage_canonical_table(float* s_tab, const float* __restrict__ table,
+                                                      const TreeProgram& prog, int nthreads) {
+    for (int i = threadIdx.x; i < prog.n_links * DRMB200_TABLE_STRIDE; i += nthreads) {
+        const int l = i / DRMB200_TABLE_STRIDE, e = i - l * DRMB200_TABLE_STRIDE;
+        const int p = prog.parent[l];
+        int src;
+        const float sg = canon_map(e, p >= 0 ? (int)prog.axis[p] : 0, prog.axis[l], src);
+        s_tab[i] = sg * __ldg(table + l * DRMB200_TABLE_STRIDE + src);
     }
 }
 
@@ -104,12 +87,13 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
     float* s_tab = smem + L.table;
     float* s_link = smem + L.link;
     float* s_slot = smem + L.slots;
+    constexpr int T = RNEA_TILE;
 
     const int tid = threadIdx.x;
-    const int64_t tile_start = (int64_t)blockIdx.x * RNEA_TILE;
-    const int valid = (int)min((int64_t)RNEA_TILE, args.batch - tile_start);
-    const bool vec_ok = args.bulk_ok;
-    const bool bulk = args.bulk_ok && ((valid & 3) == 0);
+    const int64_t tile_start = (int64_t)blockIdx.x * T;
+    const int valid = (int)min((int64_t)T, args.batch - tile_start);
+    const bool vec_ok = args.aligned;
+    const bool bulk = args.aligned && ((valid & 3) == 0);
 
     if (bulk) {
         if (tid == 0) {
@@ -126,7 +110,7 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
         coop_copy(s_qd, args.qd + tile_start * n, valid * n, vec_ok);
         coop_copy(s_qdd, args.qdd + tile_start * n, valid * n, vec_ok);
     }
-    for (int i = tid; i < N * DRMB200_TABLE_STRIDE; i += RNEA_TILE) s_tab[i] = __ldg(args.table + i);
+    stage_canonical_table(s_tab, args.table, prog, T);
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
 
@@ -141,40 +125,29 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
         // ---- pass 1: root -> leaves, motion state + body wrench ------------------------------------
         V3 w = v3(0.f, 0.f, 0.f), v = w, al = w, a = w;     // state of the previously processed link
         for (int i = 1; i < N; ++i) {
-            const LinkConsts C = load_link(s_tab + i * DRMB200_TABLE_STRIDE);
+            const LinkRow C = load_row(s_tab + i * DRMB200_TABLE_STRIDE);
             const int src = prog.psrc[i];
             V3 wp, vp, alp, ap;
             if (src == 0) { wp = w; vp = v; alp = al; ap = a; }
             else if (src < 0) { wp = vp = alp = v3(0.f, 0.f, 0.f); ap = v3(0.f, 0.f, g); }
             else {
-                const float* sl = s_slot + (src - 1) * 12 * RNEA_TILE + tid;
-                wp = v3(sl[0], sl[RNEA_TILE], sl[2 * RNEA_TILE]);
-                vp = v3(sl[3 * RNEA_TILE], sl[4 * RNEA_TILE], sl[5 * RNEA_TILE]);
-                alp = v3(sl[6 * RNEA_TILE], sl[7 * RNEA_TILE], sl[8 * RNEA_TILE]);
-                ap = v3(sl[9 * RNEA_TILE], sl[10 * RNEA_TILE], sl[11 * RNEA_TILE]);
+                const float* sl = s_slot + (src - 1) * 12 * T + tid;
+                wp = ldv(sl, T); vp = ldv(sl + 3 * T, T); alp = ldv(sl + 6 * T, T); ap = ldv(sl + 9 * T, T);
             }
             M3 M = C.F;
-            const int ax = prog.axis[i];
-            float cs = 1.f, sn = 0.f;
-            int ai = 0;
-            float qd_s = 0.f, qdd_s = 0.f;           // signed joint rate / acceleration along +e_ai
-            if (ax != 0) {
-                ai = (ax > 0 ? ax : -ax) - 1;
-                const int c = prog.dof[i];
-                float th = qrow[c];
-                qd_s = qdrow[c];
-                qdd_s = qddrow[c];
-                if (ax < 0) { th = -th; qd_s = -qd_s; qdd_s = -qdd_s; }
-                sincos_pi2(th, sn, cs);
-                apply_joint_rotation(M, ai, cs, sn);
+            const int c = prog.dof[i];
+            float cs = 1.f, sn = 0.f, qd_k = 0.f, qdd_k = 0.f;
+            if (c >= 0) {
+                qd_k = qdrow[c];
+                qdd_k = qddrow[c];
+                sincos_pi2(qrow[c], sn, cs);
+                rotate_z(M, cs, sn);
             }
-            const V3 wJ = axis_vec(ai, qd_s);
-            // velocities (robot_model.py:183-193)
-            w = mulT(M, wp) + wJ;
-            v = mulT(M, cross_add(wp, C.r, vp));                 // v_p - r x w_p = v_p + w_p x r
-            // accelerations (robot_model.py:269-277)
-            al = mulT(M, alp) + axis_vec(ai, qdd_s) + cross(w, wJ);
-            a = mulT(M, cross_add(alp, C.r, ap)) + cross(v, wJ);
+            // velocities (robot_model.py:183-193), accelerations (robot_model.py:269-277)
+            w = mulT(M, wp); w.z += qd_k;
+            v = mulT(M, cross_add(wp, C.r, vp));
+            al = mulT(M, alp) + cross_z(w, qd_k); al.z += qdd_k;
+            a = mulT(M, cross_add(alp, C.r, ap)) + cross_z(v, qd_k);
             // body wrench (robot_model.py:289-293; spatial_vector_algebra.py:321-338)
             const V3 hl_a = C.m * a - cross(C.mc, al);
             const V3 ha_a = mul_add(C.Io, al, cross(C.mc, a));
@@ -182,47 +155,37 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
             const V3 ha_v = mul_add(C.Io, w, cross(C.mc, v));
             const V3 f = cross_add(w, hl_v, hl_a);
             const V3 nn = cross_add(w, ha_v, cross_add(v, hl_v, ha_a));
-            float* lk = s_link + i * 8 * RNEA_TILE + tid;
-            lk[0] = f.x; lk[RNEA_TILE] = f.y; lk[2 * RNEA_TILE] = f.z;
-            lk[3 * RNEA_TILE] = nn.x; lk[4 * RNEA_TILE] = nn.y; lk[5 * RNEA_TILE] = nn.z;
-            lk[6 * RNEA_TILE] = cs; lk[7 * RNEA_TILE] = sn;
+            float* lk = s_link + i * 8 * T + tid;
+            stv(lk, T, f); stv(lk + 3 * T, T, nn);
+            lk[6 * T] = cs; lk[7 * T] = sn;
             const int sv = prog.save[i];
             if (sv >= 0) {
-                float* sl = s_slot + sv * 12 * RNEA_TILE + tid;
-                sl[0] = w.x; sl[RNEA_TILE] = w.y; sl[2 * RNEA_TILE] = w.z;
-                sl[3 * RNEA_TILE] = v.x; sl[4 * RNEA_TILE] = v.y; sl[5 * RNEA_TILE] = v.z;
-                sl[6 * RNEA_TILE] = al.x; sl[7 * RNEA_TILE] = al.y; sl[8 * RNEA_TILE] = al.z;
-                sl[9 * RNEA_TILE] = a.x; sl[10 * RNEA_TILE] = a.y; sl[11 * RNEA_TILE] = a.z;
+                float* sl = s_slot + sv * 12 * T + tid;
+                stv(sl, T, w); stv(sl + 3 * T, T, v); stv(sl + 6 * T, T, al); stv(sl + 9 * T, T, a);
             }
         }
 
         // ---- pass 2: leaves -> root, wrench propagation + joint torques (robot_model.py:284-301, 353-373)
         for (int i = N - 1; i >= 1; --i) {
-            const float* lk = s_link + i * 8 * RNEA_TILE + tid;
-            const V3 f = v3(lk[0], lk[RNEA_TILE], lk[2 * RNEA_TILE]);
-            const V3 nn = v3(lk[3 * RNEA_TILE], lk[4 * RNEA_TILE], lk[5 * RNEA_TILE]);
-            const int ax = prog.axis[i];
-            if (ax != 0) {
-                const int ai = (ax > 0 ? ax : -ax) - 1;
-                const int c = prog.dof[i];
-                float t = comp(nn, ai);
-                if (ax < 0) t = -t;
+            const float* lk = s_link + i * 8 * T + tid;
+            const V3 f = ldv(lk, T);
+            const V3 nn = ldv(lk + 3 * T, T);
+            const int c = prog.dof[i];
+            if (c >= 0) {
+                float t = nn.z;
                 if (damp) t = fmaf(s_tab[i * DRMB200_TABLE_STRIDE + 25], qdrow[c], t);
                 taurow[c] = t;
             }
             const int p = prog.parent[i];
             if (p > 0) {
-                const float4* t4 = reinterpret_cast<const float4*>(s_tab + i * DRMB200_TABLE_STRIDE);
-                const float4 f0 = t4[0], f1 = t4[1], f2 = t4[2];
-                M3 M; M.a00 = f0.x; M.a01 = f0.y; M.a02 = f0.z; M.a10 = f0.w; M.a11 = f1.x; M.a12 = f1.y;
-                M.a20 = f1.z; M.a21 = f1.w; M.a22 = f2.x;
-                const V3 r = v3(f2.y, f2.z, f2.w);
-                if (ax != 0) apply_joint_rotation(M, (ax > 0 ? ax : -ax) - 1, lk[6 * RNEA_TILE], lk[7 * RNEA_TILE]);
-                const V3 fp = mul(M, f);                           // SpatialForceVec.transform (sva:281-291)
-                const V3 np = cross_add(r, fp, mul(M, nn));
-                float* pk = s_link + p * 8 * RNEA_TILE + tid;
-                pk[0] += fp.x; pk[RNEA_TILE] += fp.y; pk[2 * RNEA_TILE] += fp.z;
-                pk[3 * RNEA_TILE] += np.x; pk[4 * RNEA_TILE] += np.y; pk[5 * RNEA_TILE] += np.z;
+                M3 F; V3 r;
+                load_Fr(s_tab + i * DRMB200_TABLE_STRIDE, F, r);
+                const float cs = lk[6 * T], sn = lk[7 * T];
+                const V3 fp = mul(F, rotz(f, cs, sn));              // M f = F~ (Rz f)  (sva:281-291)
+                const V3 np = cross_add(r, fp, mul(F, rotz(nn, cs, sn)));
+                float* pk = s_link + p * 8 * T + tid;
+                pk[0] += fp.x; pk[T] += fp.y; pk[2 * T] += fp.z;
+                pk[3 * T] += np.x; pk[4 * T] += np.y; pk[5 * T] += np.z;
             }
         }
     }
@@ -261,10 +224,10 @@ int build_tree_program(const drmb200_topology_t* topo, TreeProgram* prog) {
         if (ax != 0 && (topo->dof[i] < 0 || topo->dof[i] >= topo->n_dofs)) { set_error("link %d: bad dof %d", i, (int)topo->dof[i]); return DRMB200_EINVAL; }
         prog->parent[i] = (int8_t)p;
         prog->axis[i] = (int8_t)ax;
-        prog->dof[i] = topo->dof[i];
+        prog->dof[i] = (ax != 0) ? topo->dof[i] : (int8_t)-1;
         if (p != i - 1 && p != 0) last_far_child[p] = i;
     }
-    prog->parent[0] = -1; prog->axis[0] = 0; prog->dof[0] = -1; prog->psrc[0] = -1; prog->save[0] = -1;
+    prog->parent[0] = -1; prog->axis[0] = 0; prog->dof[0] = -1; prog->psrc[0] = -1; prog->save[0] = -1; prog->accw[0] = 0;
     int slot_of[DRMB200_MAX_LINKS];
     int slot_free_after[DRM_MAX_SLOTS];
     for (int s = 0; s < DRM_MAX_SLOTS; ++s) slot_free_after[s] = -1;
@@ -273,6 +236,7 @@ int build_tree_program(const drmb200_topology_t* topo, TreeProgram* prog) {
         const int p = topo->parent[i];
         prog->psrc[i] = (p == 0) ? -1 : (p == i - 1 ? 0 : (int8_t)(1 + slot_of[p]));
         prog->save[i] = -1;
+        prog->accw[i] = (p == 0 || p == i - 1) ? 0 : (last_far_child[p] == i ? 2 : 1);
         if (last_far_child[i] >= 0) {
             int s = 0;
             while (s < DRM_MAX_SLOTS && slot_free_after[s] >= i) ++s;
@@ -301,7 +265,7 @@ int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     RneaArgs args;
     args.table = table; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    args.bulk_ok = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
+    args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
 
     const RneaSmemLayout L(prog.n_dofs, prog.n_links, prog.n_slots);
     const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);

@@ -167,6 +167,7 @@ class FkJacobianFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, table, q, topo, ee_link, want_pos, want_quat, want_jac):
+        table, q = table.contiguous(), q.contiguous()
         pos, quat, jlin, jang = fk_jacobian_raw(topo, ee_link, table, q, want_pos, want_quat, want_jac)
         ctx.save_for_backward(table, q)
         ctx.topo, ctx.ee_link = topo, ee_link
@@ -197,6 +198,7 @@ class InverseDynamicsFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, table, q, qd, qdd, topo, flags):
+        table, q, qd, qdd = table.contiguous(), q.contiguous(), qd.contiguous(), qdd.contiguous()
         tau = inverse_dynamics_raw(topo, table, q, qd, qdd, flags)
         ctx.save_for_backward(table, q, qd, qdd)
         ctx.topo, ctx.flags = topo, flags
@@ -216,8 +218,7 @@ class InverseDynamicsFunction(torch.autograd.Function):
         ws = _workspace(ctx.topo, B, q.device)
         with torch.cuda.device(q.device):
             rc = lib().drmb200_inverse_dynamics_backward(
-                ctypes.byref(ctx.topo), _ptr(table), _ptr(q.contiguous()), _ptr(qd.contiguous()),
-                _ptr(qdd.contiguous()), B, ctx.flags, _ptr(g_tau), _ptr(q_grad), _ptr(qd_grad), _ptr(qdd_grad),
+                ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B, ctx.flags, _ptr(g_tau), _ptr(q_grad), _ptr(qd_grad), _ptr(qdd_grad),
                 _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_inverse_dynamics_backward")
         return table_grad, q_grad, qd_grad, qdd_grad, None, None

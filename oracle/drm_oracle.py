@@ -302,3 +302,34 @@ def sample_inputs(robot, batch, seed=0, dtype=torch.float32, vel_scale=0.2, acc_
     qd = (2 * u[1] - 1) * vel_scale * vel
     qdd = (2 * u[2] - 1) * acc_scale * vel
     return q.to(dtype), qd.to(dtype), qdd.to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------
+# flat-table view (layout of include/drm_b200.h) -- used to check the kernels' table gradients
+# ------------------------------------------------------------------------------------------------
+def axis_codes(robot):
+    """0 fixed, +-1/+-2/+-3 = +-x/+-y/+-z per link."""
+    codes = []
+    for i in range(len(robot.names)):
+        if robot.dof[i] < 0:
+            codes.append(0)
+            continue
+        ax = robot.axis[i]
+        k = int(torch.where(ax != 0)[0])
+        codes.append((k + 1) if float(ax[k]) > 0 else -(k + 1))
+    return codes
+
+
+def link_table(robot):
+    """Differentiable [N,28] table [F(9) r(3) Io(9) mc(3) m d 0 0] from the Robot parameters."""
+    rows = []
+    for i in range(len(robot.names)):
+        roll, pitch, yaw = robot.rpy[i, 0:1], robot.rpy[i, 1:2], robot.rpy[i, 2:3]
+        F = ((_elem_rot(2, yaw) @ _elem_rot(1, pitch)) @ _elem_rot(0, roll))[0]
+        c = robot.com[i:i + 1]
+        S = _skew(c)[0]
+        Io = robot.inertia[i] + robot.mass[i] * (S @ S.T)
+        rows.append(torch.cat([F.reshape(9), robot.trans[i], Io.reshape(9), robot.mass[i] * robot.com[i],
+                               robot.mass[i].reshape(1), robot.damping[i].reshape(1),
+                               torch.zeros(2, dtype=robot.trans.dtype)]))
+    return torch.stack(rows)

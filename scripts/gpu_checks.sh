@@ -12,7 +12,9 @@ echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' 
 
 echo "== bench (TMA bulk staging)"; timeout 600 python bench.py 2> gpurun_out/bench.err | tee gpurun_out/bench.json
 tail -3 gpurun_out/bench.err
-echo "== bench (cooperative staging)"; DRMB200_FK_VARIANT=0 timeout 300 python bench.py --no-cpu-baseline --no-e2e 2>> gpurun_out/bench.err | tee gpurun_out/bench_coop.json
+for tile in 64 128 256; do
+  echo "== bench fk_tile=$tile"; DRMB200_FK_TILE=$tile timeout 300 python bench.py --no-cpu-baseline --no-e2e 2>> gpurun_out/bench.err | tee gpurun_out/bench_tile$tile.json
+done
 if [ "${1:-}" = "quick" ]; then exit 0; fi
 
 echo "== reference arm"; timeout 400 python bench.py --impl reference --steps 20 --warmup 3 2>> gpurun_out/bench.err | tee gpurun_out/bench_reference.json

@@ -122,3 +122,64 @@ def test_known_answers():
     tau = O.inverse_dynamics(robot, q, qd, qdd, False, False)
     assert_close(tau.numpy(), [[-0.01230314, -0.09288787, -0.00786535, 0.03695315, -0.00435376, -0.00580134,
                                 -0.00109955]], atol=1e-5, what="tau no gravity")
+
+
+# ------------------------------------------------------------------------------------------------
+# the analytic adjoint recursions the backward kernels implement (oracle/adjoint_proto.py)
+# ------------------------------------------------------------------------------------------------
+from oracle import adjoint_proto as A  # noqa: E402
+
+_PARAMS = ("trans", "rpy", "mass", "com", "inertia", "damping")
+
+
+def _param_grads_via_table(robot, table_grad):
+    table = O.link_table(robot)
+    return torch.autograd.grad(table, [getattr(robot, p) for p in _PARAMS], grad_outputs=table_grad, allow_unused=True)
+
+
+@pytest.mark.parametrize("stem", ["2link_robot", "iiwa7", "allegro_hand_description_left", "trifinger_edu",
+                                  "jaco_clean", "fetch_arm_no_gripper", "iiwa7_allegro"])
+def test_adjoint_recursions_match_autograd(stem):
+    g = load_golden(stem)
+    dt = torch.float64
+    q, qd, qdd = (t[:5].clone().requires_grad_(True) for t in _inputs(g, dt))
+    gen = torch.Generator().manual_seed(5)
+    robot = _grad_robot(stem, dt)
+    codes = O.axis_codes(robot)
+    n = robot.n_dofs
+
+    # inverse dynamics, all four flag combinations
+    for grav, damp in ((True, True), (False, True), (True, False), (False, False)):
+        G = torch.randn(5, n, generator=gen, dtype=dt)
+        tau = O.inverse_dynamics(robot, q, qd, qdd, grav, damp)
+        want = torch.autograd.grad((G * tau).sum(), [q, qd, qdd] + [getattr(robot, p) for p in _PARAMS],
+                                   allow_unused=True)
+        table = O.link_table(robot).detach()
+        dq, dqd, dqdd, tg = A.inverse_dynamics_backward(table, robot.parent, codes, robot.dof, q.detach(), qd.detach(),
+                                                        qdd.detach(), G, grav, damp)
+        for got, w, name in zip((dq, dqd, dqdd), want[:3], ("q", "qd", "qdd")):
+            assert_close(got.numpy(), w.numpy(), rtol=1e-9, atol=1e-9, what=f"{stem} id d{name}")
+        for got, w, name in zip(_param_grads_via_table(robot, tg), want[3:], _PARAMS):
+            w = torch.zeros_like(getattr(robot, name)) if w is None else w
+            got = torch.zeros_like(w) if got is None else got
+            assert_close(got[1:].numpy(), w[1:].numpy(), rtol=1e-9, atol=1e-9, what=f"{stem} id d{name}")
+
+    # FK + Jacobian (+ quaternion) of every golden link
+    for link in g["fk_links"].tolist():
+        e = robot.index(link)
+        Gp, Gq = torch.randn(5, 3, generator=gen, dtype=dt), torch.randn(5, 4, generator=gen, dtype=dt)
+        Gl, Ga = torch.randn(5, 3, n, generator=gen, dtype=dt), torch.randn(5, 3, n, generator=gen, dtype=dt)
+        pos, quat = O.forward_kinematics(robot, q, link)
+        jl, ja = O.jacobian(robot, q, link)
+        loss = (Gp * pos).sum() + (Gq * quat).sum() + (Gl * jl).sum() + (Ga * ja).sum()
+        want = torch.autograd.grad(loss, [q] + [getattr(robot, p) for p in _PARAMS], allow_unused=True)
+        table = O.link_table(robot).detach()
+        dq, tg = A.fk_jacobian_backward(table, robot.parent, codes, robot.dof, e, q.detach(), Gp, Gq, Gl, Ga)
+        assert_close(dq.numpy(), want[0].numpy(), rtol=1e-9, atol=1e-9, what=f"{stem} fk dq {link}")
+        for got, w, name in zip(_param_grads_via_table(robot, tg), want[1:], _PARAMS):
+            if name in ("trans", "rpy"):
+                w = torch.zeros_like(getattr(robot, name)) if w is None else w
+                # fixed-joint origins: the oracle (like the reference) treats them as constants baked in at
+                # construction, the table carries their gradient -- compare movable links only
+                mov = [i for i in range(len(robot.names)) if robot.dof[i] >= 0]
+                assert_close(got[mov].numpy(), w[mov].numpy(), rtol=1e-9, atol=1e-9, what=f"{stem} fk d{name} {link}")
