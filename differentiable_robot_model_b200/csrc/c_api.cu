@@ -14,7 +14,7 @@ namespace drm {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-static std::atomic<int> g_options[2] = {{-1}, {-1}};   // 0: fk_variant, 1: fk_tile
+static std::atomic<int> g_options[3] = {{-1}, {-1}, {-1}};   // 0: fk_variant, 1: fk_tile, 2: fk_unroll
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -27,11 +27,14 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // Tuning knobs for A/B measurements, overridable with the environment or drmb200_set_option():
 //   0 "fk_variant" (DRMB200_FK_VARIANT): 1 = TMA bulk-copy staging (default), 0 = cooperative float4 copies
 //   1 "fk_tile"    (DRMB200_FK_TILE):    configurations per CTA, 64 / 128 / 256; 0 = pick by batch size
+//   2 "fk_unroll"  (DRMB200_FK_UNROLL):  1 = unrolled register-Jacobian kernel for paths <= 8 links (default), 0 = rolled
 int get_option(int which) {
     int v = g_options[which].load(std::memory_order_relaxed);
     if (v < 0) {
-        const char* e = getenv(which == 0 ? "DRMB200_FK_VARIANT" : "DRMB200_FK_TILE");
-        v = e ? atoi(e) : (which == 0 ? 1 : 0);
+        static const char* names[3] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL"};
+        static const int defaults[3] = {1, 0, 1};
+        const char* e = getenv(names[which]);
+        v = e ? atoi(e) : defaults[which];
         g_options[which].store(v, std::memory_order_relaxed);
     }
     return v;
@@ -100,9 +103,10 @@ static int fk_jacobian_host_impl(const drmb200_topology_t* topo, int32_t ee_link
     const int n = topo->n_dofs;
     std::lock_guard<std::mutex> lock(g_pipe_mu);
     CK(cudaSetDevice(device));
-    // 64 Ki configurations per chunk: 14.7 MB per stage for a 7-DoF arm, large enough for PCIe
-    // efficiency, small enough that three stages overlap H2D / compute / D2H.
-    const int64_t want_chunk = 65536;
+    // 16 Ki configurations per chunk: 3.7 MB per stage for a 7-DoF arm -- large enough for PCIe
+    // efficiency, small enough that a 64 Ki-configuration call already overlaps the H2D of chunk k+1
+    // with the kernel of chunk k and the D2H of chunk k-1 on the three stage streams.
+    const int64_t want_chunk = 16384;
     if (g_pipe.device != device || g_pipe.n_dofs != n || g_pipe.chunk != want_chunk) {
         g_pipe.release();
         g_pipe.device = device;
@@ -153,6 +157,7 @@ int64_t drmb200_launch_count(void) { return drm::g_launches.load(); }
 int drmb200_set_option(const char* name, int value) {
     if (name != nullptr && std::string(name) == "fk_variant") { drm::g_options[0].store(value); return DRMB200_OK; }
     if (name != nullptr && std::string(name) == "fk_tile") { drm::g_options[1].store(value); return DRMB200_OK; }
+    if (name != nullptr && std::string(name) == "fk_unroll") { drm::g_options[2].store(value); return DRMB200_OK; }
     drm::set_error("unknown option");
     return DRMB200_EINVAL;
 }

@@ -57,7 +57,26 @@ struct FkSmemLayout {
     }
 };
 
-template <int NDOF, int TILE, bool WITH_JAC>
+// One link of the chain walk: p <- R r + p ; R <- R F~ ; for movable joints record the joint axis
+// z (third column, unchanged by the z rotation) and m = z x p_i, then R <- R Rz(q).
+template <bool FIRST, bool WITH_JAC>
+__device__ __forceinline__ void walk_link(const float* row, const float* qrow, int c, M3& R, V3& p, V3& z, V3& m) {
+    M3 F; V3 r;
+    load_Fr(row, F, r);
+    if (FIRST) { p = r; R = F; }             // parent is the root: R = I, p = 0
+    else { p = mul_add(R, r, p); R = mul(R, F); }
+    if (c >= 0) {
+        float sn, cs;
+        sincos_pi2(qrow[c], sn, cs);
+        if (WITH_JAC) { z = col2(R); m = cross(z, p); }
+        rotate_z(R, cs, sn);
+    }
+}
+
+// MAXLEN > 0: paths of at most MAXLEN links, loops fully unrolled, the Jacobian columns (z_i, z_i x p_i)
+//             wait in REGISTERS for p_ee and are written to the smem tile exactly once;
+// MAXLEN = 0: any path length, rolled loop, columns parked in the smem tile and fixed up in a second pass.
+template <int NDOF, int TILE, bool WITH_JAC, int MAXLEN>
 __global__ void __launch_bounds__(TILE)
 fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) {
     extern __shared__ __align__(128) float smem[];
@@ -92,12 +111,11 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
     } else {
         coop_copy(s_q, args.q + tile_start * n, valid * n, vec_ok);
     }
-    // canonical (F~, r~) rows of the path links -> smem
+    // canonical (F~, r~) rows of the path links -> smem (signed gather, map precomputed on the host)
     for (int i = tid; i < len * 12; i += TILE) {
-        const int k = i / 12, e = i - k * 12;
-        int src;
-        const float sg = canon_map(e, prog.paxis[k], prog.axis[k], src);
-        s_tab[i] = sg * __ldg(args.table + (int)prog.link[k] * DRMB200_TABLE_STRIDE + src);
+        const uint32_t mp = prog.tab_map[i];
+        const float v = __ldg(args.table + (mp & 0x7fffu));
+        s_tab[i] = (mp & 0x8000u) ? -v : v;
     }
     if (WITH_JAC && !prog.full_cover) {      // columns of joints off the path stay zero
         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -115,38 +133,57 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
         float* jl = s_jlin + tid * 3 * n;
         float* ja = s_jang + tid * 3 * n;
 
-        for (int k = 0; k < len; ++k) {
-            M3 F; V3 r;
-            load_Fr(s_tab + k * 12, F, r);
-            p = mul_add(R, r, p);            // p_i = R_parent r_i + p_parent
-            R = mul(R, F);                   // R_parent F_i
-            const int c = prog.dof[k];
-            if (c >= 0) {
-                float sn, cs;
-                sincos_pi2(qrow[c], sn, cs);
-                if (WITH_JAC) {
-                    const V3 z = col2(R);    // joint axis in the world frame (unchanged by Rz)
-                    const V3 m = cross(z, p);
+        if (MAXLEN > 0) {
+            V3 zs[MAXLEN > 0 ? MAXLEN : 1], ms[MAXLEN > 0 ? MAXLEN : 1];
+#pragma unroll
+            for (int k = 0; k < MAXLEN; ++k) {
+                zs[k] = ms[k] = v3(0.f, 0.f, 0.f);
+                if (k < len) {
+                    if (k == 0) walk_link<true, WITH_JAC>(s_tab, qrow, prog.dof[0], R, p, zs[0], ms[0]);
+                    else walk_link<false, WITH_JAC>(s_tab + k * 12, qrow, prog.dof[k], R, p, zs[k], ms[k]);
+                }
+            }
+            if (WITH_JAC) {
+                // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
+#pragma unroll
+                for (int k = 0; k < MAXLEN; ++k) {
+                    if (k < len) {
+                        const int c = prog.dof[k];
+                        if (c >= 0) {
+                            const V3 z = zs[k];
+                            const V3 j = cross_add(z, p, v3(-ms[k].x, -ms[k].y, -ms[k].z));
+                            ja[c] = z.x; ja[n + c] = z.y; ja[2 * n + c] = z.z;
+                            jl[c] = j.x; jl[n + c] = j.y; jl[2 * n + c] = j.z;
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int k = 0; k < len; ++k) {
+                V3 z, m;
+                const int c = prog.dof[k];
+                walk_link<false, WITH_JAC>(s_tab + k * 12, qrow, c, R, p, z, m);
+                if (WITH_JAC && c >= 0) {
                     ja[c] = z.x; ja[n + c] = z.y; ja[2 * n + c] = z.z;
                     jl[c] = m.x; jl[n + c] = m.y; jl[2 * n + c] = m.z;
                 }
-                rotate_z(R, cs, sn);
+            }
+            if (WITH_JAC) {
+                for (int k = 0; k < len; ++k) {
+                    const int c = prog.dof[k];
+                    if (c < 0) continue;
+                    const V3 z = v3(ja[c], ja[n + c], ja[2 * n + c]);
+                    const V3 m = v3(jl[c], jl[n + c], jl[2 * n + c]);
+                    const V3 j = cross_add(z, p, v3(-m.x, -m.y, -m.z));
+                    jl[c] = j.x; jl[n + c] = j.y; jl[2 * n + c] = j.z;
+                }
             }
         }
 
         if (args.pos != nullptr) { s_pos[tid * 3 + 0] = p.x; s_pos[tid * 3 + 1] = p.y; s_pos[tid * 3 + 2] = p.z; }
-        if (args.quat != nullptr) reinterpret_cast<float4*>(s_quat)[tid] = quat_xyzw(unpermute_cols(R, prog.ee_axis));
-
-        if (WITH_JAC) {
-            // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
-            for (int k = 0; k < len; ++k) {
-                const int c = prog.dof[k];
-                if (c < 0) continue;
-                const V3 z = v3(ja[c], ja[n + c], ja[2 * n + c]);
-                const V3 m = v3(jl[c], jl[n + c], jl[2 * n + c]);
-                const V3 j = cross_add(z, p, v3(-m.x, -m.y, -m.z));
-                jl[c] = j.x; jl[n + c] = j.y; jl[2 * n + c] = j.z;
-            }
+        if (args.quat != nullptr) {
+            if (prog.ee_axis != 0) R = unpermute_cols(R, prog.ee_axis);     // uniform; fixed ee links skip it
+            reinterpret_cast<float4*>(s_quat)[tid] = quat_xyzw(R);
         }
     }
 
@@ -217,17 +254,22 @@ int build_path_program(const drmb200_topology_t* topo, int32_t ee_link, PathProg
             ++covered;
         }
         if (k == len - 1) prog->ee_axis = ax;
+        for (int e = 0; e < 12; ++e) {          // signed gather map of the canonical (F~, r~) row
+            int src;
+            const float sg = canon_map(e, prog->paxis[k], ax, src);
+            prog->tab_map[k * 12 + e] = (uint16_t)((l * DRMB200_TABLE_STRIDE + src) | (sg < 0.f ? 0x8000 : 0));
+        }
     }
     prog->full_cover = (covered == topo->n_dofs) ? 1 : 0;
     return DRMB200_OK;
 }
 
-template <int NDOF, int TILE, bool WITH_JAC>
+template <int NDOF, int TILE, bool WITH_JAC, int MAXLEN>
 static int launch_fk(const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
     const FkSmemLayout L(TILE, prog.n_dofs, prog.len, WITH_JAC);
     const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("fk kernel needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
-    auto kern = fk_jacobian_kernel<NDOF, TILE, WITH_JAC>;
+    auto kern = fk_jacobian_kernel<NDOF, TILE, WITH_JAC, MAXLEN>;
     static size_t configured_by_dev[64] = {0};     // per instantiation, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -246,9 +288,15 @@ static int launch_fk(const PathProgram& prog, const FkArgs& args, cudaStream_t s
     return DRMB200_OK;
 }
 
+template <int NDOF, int TILE, bool WITH_JAC>
+static int launch_fk_l(const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
+    const bool unrolled = prog.len <= 8 && get_option(2) != 0;
+    return unrolled ? launch_fk<NDOF, TILE, WITH_JAC, 8>(prog, args, stream)
+                    : launch_fk<NDOF, TILE, WITH_JAC, 0>(prog, args, stream);
+}
 template <int NDOF, int TILE>
 static int launch_fk_j(bool with_jac, const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
-    return with_jac ? launch_fk<NDOF, TILE, true>(prog, args, stream) : launch_fk<NDOF, TILE, false>(prog, args, stream);
+    return with_jac ? launch_fk_l<NDOF, TILE, true>(prog, args, stream) : launch_fk_l<NDOF, TILE, false>(prog, args, stream);
 }
 template <int NDOF>
 static int launch_fk_t(int tile, bool with_jac, const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {

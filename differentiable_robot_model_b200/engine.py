@@ -171,9 +171,7 @@ class FkJacobianFunction(torch.autograd.Function):
         pos, quat, jlin, jang = fk_jacobian_raw(topo, ee_link, table, q, want_pos, want_quat, want_jac)
         ctx.save_for_backward(table, q)
         ctx.topo, ctx.ee_link = topo, ee_link
-        outs = (pos, quat, jlin, jang)
-        ctx.mark_non_differentiable(*[o for o in outs if o is None])
-        return outs
+        return pos, quat, jlin, jang           # skipped outputs are None
 
     @staticmethod
     def backward(ctx, g_pos, g_quat, g_jlin, g_jang):

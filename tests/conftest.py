@@ -30,6 +30,10 @@ URDFS = {
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the CPU oracle issues thousands of tiny torch ops: on a 128-core host the default intra-op
+    # thread count makes each of them slower, not faster
+    import torch
+    torch.set_num_threads(min(8, os.cpu_count() or 1))
 
 
 def urdf_path(stem):

@@ -1,0 +1,46 @@
+"""CPU: pin the C oracle (oracle/drm_oracle.c, float and double builds) against the golden vectors
+generated from the reference itself, and against the torch oracle on a larger seeded batch."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close, canon_quat, load_golden, urdf_path
+from oracle import drm_oracle as O
+from oracle.c_oracle import CRobot
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_c_oracle_matches_reference_golden(robot_stem, dtype):
+    g = load_golden(robot_stem)
+    robot = O.load_robot(urdf_path(robot_stem), torch.float64)
+    c = CRobot(robot, dtype)
+    for link in g["fk_links"].tolist():
+        pos, quat, jl, ja = c.fk_jacobian(robot.index(link), g["q"])
+        assert_close(pos, g[f"pos.{link}"], what=f"pos {link}")
+        assert_close(canon_quat(quat), canon_quat(g[f"quat.{link}"]), what=f"quat {link}")
+        assert_close(jl, g[f"jlin.{link}"], what=f"jlin {link}")
+        assert_close(ja, g[f"jang.{link}"], what=f"jang {link}")
+    for grav in (0, 1):
+        for damp in (0, 1):
+            tau = c.inverse_dynamics(g["q"], g["qd"], g["qdd"], grav, damp)
+            scale = float(np.abs(g[f"tau.g{grav}d{damp}"]).max())
+            assert_close(tau, g[f"tau.g{grav}d{damp}"], rtol=1e-5, atol=max(1e-5, 2e-6 * scale), what=f"tau g{grav}d{damp}")
+
+
+def test_c_oracle_matches_torch_oracle_and_is_thread_count_independent():
+    robot = O.load_robot(urdf_path("allegro_hand_description_left"), torch.float64)
+    q, qd, qdd = O.sample_inputs(robot, 3001, seed=5, dtype=torch.float64)
+    c = CRobot(robot, np.float64)
+    e = robot.index("link_3.0_tip")
+    outs1 = c.fk_jacobian(e, q.numpy(), n_threads=1)
+    outs8 = c.fk_jacobian(e, q.numpy(), n_threads=8)
+    for a, b in zip(outs1, outs8):
+        np.testing.assert_array_equal(a, b)
+    pos, quat = O.forward_kinematics(robot, q, "link_3.0_tip")
+    jl, ja = O.jacobian(robot, q, "link_3.0_tip")
+    assert_close(outs1[0], pos.numpy(), rtol=1e-10, atol=1e-12, what="pos")
+    assert_close(canon_quat(outs1[1]), canon_quat(quat.numpy()), rtol=1e-10, atol=1e-12, what="quat")
+    assert_close(outs1[2], jl.numpy(), rtol=1e-10, atol=1e-12, what="jlin")
+    assert_close(outs1[3], ja.numpy(), rtol=1e-10, atol=1e-12, what="jang")
+    tau = c.inverse_dynamics(q.numpy(), qd.numpy(), qdd.numpy())
+    assert_close(tau, O.inverse_dynamics(robot, q, qd, qdd).numpy(), rtol=1e-9, atol=1e-10, what="tau")
