@@ -23,26 +23,28 @@
 
 namespace drm {
 
-constexpr int BWD_TILE = 128;                 // configurations per CTA per tile == threads per CTA
+// configurations per CTA per tile == threads per CTA: a template parameter T in {128, 64, 32}, the largest
+// whose shared-memory footprint fits (big trees such as the 21-link Allegro hand need the smaller tiles)
 constexpr int BWD_MAX_GRID = 148 * 8;         // upper bound of persistent CTAs (workspace sizing)
-constexpr int SCR_LD = BWD_TILE + 1;          // padded leading dimension of the reduction scratch
+constexpr size_t BWD_SMEM_BUDGET = 200 * 1024;
 constexpr float GRAVITY_B = 9.81f;
 
 // ---------------------------------------------------------------------------------------------
 // block-level sum of NV per-thread values into the CTA accumulator row `acc_row` (entries map(j))
 // ---------------------------------------------------------------------------------------------
-template <int NV, typename Map>
+template <int NV, int T, typename Map>
 __device__ __forceinline__ void block_accumulate(float* scratch, float* acc_row, const float (&vals)[NV], bool active,
                                                  Map map) {
+    constexpr int SCR_LD = T + 1;             // padded leading dimension of the reduction scratch
     const int tid = threadIdx.x;
 #pragma unroll
     for (int j = 0; j < NV; ++j) scratch[j * SCR_LD + tid] = active ? vals[j] : 0.f;
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    for (int j = warp; j < NV; j += BWD_TILE / 32) {
+    for (int j = warp; j < NV; j += T / 32) {
         float x = 0.f;
 #pragma unroll
-        for (int c = 0; c < BWD_TILE / 32; ++c) x += scratch[j * SCR_LD + lane + 32 * c];
+        for (int c = 0; c < T / 32; ++c) x += scratch[j * SCR_LD + lane + 32 * c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (lane == 0) acc_row[map(j)] += x;
@@ -54,7 +56,7 @@ __device__ __forceinline__ void tile_load_or_zero(float* dst, const float* src, 
     if (src != nullptr) {
         coop_copy(dst, src, nfloats, vec_ok);
     } else {
-        for (int i = threadIdx.x; i < total; i += BWD_TILE) dst[i] = 0.f;
+        for (int i = threadIdx.x; i < total; i += blockDim.x) dst[i] = 0.f;
     }
 }
 
@@ -114,28 +116,28 @@ struct FkBwdArgs {
 
 struct FkBwdSmem {
     int q, qg, gpos, gquat, gjl, gja, table, link, scratch, acc, total_floats;
-    __host__ __device__ FkBwdSmem(int n, int len) {
+    __host__ __device__ FkBwdSmem(int tile, int n, int len) {
         int o = 0;
-        gquat = o; o += BWD_TILE * 4;
-        q = o; o += BWD_TILE * n;
-        qg = o; o += BWD_TILE * n;
-        gpos = o; o += BWD_TILE * 3;
-        gjl = o; o += BWD_TILE * 3 * n;
-        gja = o; o += BWD_TILE * 3 * n;
+        gquat = o; o += tile * 4;
+        q = o; o += tile * n;
+        qg = o; o += tile * n;
+        gpos = o; o += tile * 3;
+        gjl = o; o += tile * 3 * n;
+        gja = o; o += tile * 3 * n;
         table = o; o += len * 12;
-        link = o; o += len * 14 * BWD_TILE;              // per path link: R~ (9), p (3), cos, sin -- slot-major
-        scratch = o; o += 12 * SCR_LD;
+        link = o; o += len * 14 * tile;                  // per path link: R~ (9), p (3), cos, sin -- slot-major
+        scratch = o; o += 12 * (tile + 1);
         acc = o; o += len * 12;                          // canonical (F~, r~) gradient per path link
         total_floats = o;
     }
 };
 
-template <bool NEED_TABLE>
-__global__ void __launch_bounds__(BWD_TILE, 2)
+template <bool NEED_TABLE, int T>
+__global__ void __launch_bounds__(T)
 fk_jacobian_backward_kernel(const __grid_constant__ PathProgram prog, const FkBwdArgs args) {
     extern __shared__ __align__(128) float smem[];
     const int n = prog.n_dofs, len = prog.len;
-    const FkBwdSmem L(n, len);
+    const FkBwdSmem L(T, n, len);
     float* s_q = smem + L.q;
     float* s_qg = smem + L.qg;
     float* s_gpos = smem + L.gpos;
@@ -148,7 +150,6 @@ fk_jacobian_backward_kernel(const __grid_constant__ PathProgram prog, const FkBw
     float* s_acc = smem + L.acc;
     const int tid = threadIdx.x;
     const bool vec_ok = args.vec_ok;
-    constexpr int T = BWD_TILE;
 
     for (int i = tid; i < len * 12; i += T) {
         const int k = i / 12, e = i - k * 12;
@@ -234,7 +235,7 @@ fk_jacobian_backward_kernel(const __grid_constant__ PathProgram prog, const FkBw
                 float vals[12];
                 m3_to_array(Fbar, vals);
                 vals[9] = rbar.x; vals[10] = rbar.y; vals[11] = rbar.z;
-                block_accumulate<12>(s_scr, s_acc + k * 12, vals, active, [](int j) { return j; });
+                block_accumulate<12, T>(s_scr, s_acc + k * 12, vals, active, [](int j) { return j; });
             }
             Rbar = Rbar_P;
             Rk = RP;
@@ -270,20 +271,20 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 
 int64_t table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch) {
     if (topo == nullptr || topo->n_links < 1 || topo->n_links > DRMB200_MAX_LINKS) return 0;
-    int64_t tiles = (batch + BWD_TILE - 1) / BWD_TILE;
+    int64_t tiles = (batch + 31) / 32;            // smallest tile the launchers may pick
     if (tiles < 1) tiles = 1;
     const int64_t grid = tiles < BWD_MAX_GRID ? tiles : BWD_MAX_GRID;
     return grid * topo->n_links * DRMB200_TABLE_STRIDE * (int64_t)sizeof(float);
 }
 
 template <typename Kern>
-static int persistent_grid(Kern kern, size_t smem_bytes, int64_t tiles, int* grid_out, const char* what) {
+static int persistent_grid(Kern kern, int block, size_t smem_bytes, int64_t tiles, int* grid_out, const char* what) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute(%zu B smem): %s", what, smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BWD_TILE, smem_bytes);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, block, smem_bytes);
     if (e != cudaSuccess || per_sm < 1) { set_error("%s: kernel does not fit on an SM (%zu B smem)", what, smem_bytes); return DRMB200_ECUDA; }
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > BWD_MAX_GRID) grid = BWD_MAX_GRID;
@@ -321,21 +322,22 @@ int fk_jacobian_backward_device(const drmb200_topology_t* topo, int32_t ee_link,
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.vec_ok = (al16(q) && al16(g_pos) && al16(g_quat) && al16(g_jl) && al16(g_ja) && al16(q_grad)) ? 1 : 0;
 
-    const FkBwdSmem L(prog.n_dofs, prog.len);
-    const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
+    int tile = 128;
+    while (tile > 32 && (size_t)FkBwdSmem(tile, prog.n_dofs, prog.len).total_floats * sizeof(float) > BWD_SMEM_BUDGET) tile >>= 1;
+    const size_t smem_bytes = (size_t)FkBwdSmem(tile, prog.n_dofs, prog.len).total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("fk backward needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
-    const int64_t tiles = (batch + BWD_TILE - 1) / BWD_TILE;
+    const int64_t tiles = (batch + tile - 1) / tile;
     int grid = 0;
     const bool need_table = table_grad != nullptr;
-    if (need_table) {
-        rc = persistent_grid(fk_jacobian_backward_kernel<true>, smem_bytes, tiles, &grid, "fk backward");
-        if (rc != DRMB200_OK) return rc;
-        fk_jacobian_backward_kernel<true><<<grid, BWD_TILE, smem_bytes, stream>>>(prog, args);
-    } else {
-        rc = persistent_grid(fk_jacobian_backward_kernel<false>, smem_bytes, tiles, &grid, "fk backward");
-        if (rc != DRMB200_OK) return rc;
-        fk_jacobian_backward_kernel<false><<<grid, BWD_TILE, smem_bytes, stream>>>(prog, args);
-    }
+#define DRM_LAUNCH_FKB(NT, TT)                                                                                  \
+    do {                                                                                                        \
+        rc = persistent_grid(fk_jacobian_backward_kernel<NT, TT>, TT, smem_bytes, tiles, &grid, "fk backward"); \
+        if (rc != DRMB200_OK) return rc;                                                                        \
+        fk_jacobian_backward_kernel<NT, TT><<<grid, TT, smem_bytes, stream>>>(prog, args);                      \
+    } while (0)
+    if (need_table) { if (tile == 128) DRM_LAUNCH_FKB(true, 128); else if (tile == 64) DRM_LAUNCH_FKB(true, 64); else DRM_LAUNCH_FKB(true, 32); }
+    else            { if (tile == 128) DRM_LAUNCH_FKB(false, 128); else if (tile == 64) DRM_LAUNCH_FKB(false, 64); else DRM_LAUNCH_FKB(false, 32); }
+#undef DRM_LAUNCH_FKB
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("fk backward launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
@@ -365,30 +367,30 @@ constexpr int LSTATE = 20;
 
 struct RneaBwdSmem {
     int q, qd, qdd, g, qg, qdg, qddg, table, link, slots, scratch, acc, total_floats;
-    __host__ __device__ RneaBwdSmem(int n, int n_links, int n_slots) {
+    __host__ __device__ RneaBwdSmem(int tile, int n, int n_links, int n_slots) {
         int o = 0;
-        q = o; o += BWD_TILE * n;
-        qd = o; o += BWD_TILE * n;
-        qdd = o; o += BWD_TILE * n;
-        g = o; o += BWD_TILE * n;
-        qg = o; o += BWD_TILE * n;
-        qdg = o; o += BWD_TILE * n;
-        qddg = o; o += BWD_TILE * n;
+        q = o; o += tile * n;
+        qd = o; o += tile * n;
+        qdd = o; o += tile * n;
+        g = o; o += tile * n;
+        qg = o; o += tile * n;
+        qdg = o; o += tile * n;
+        qddg = o; o += tile * n;
         table = o; o += n_links * DRMB200_TABLE_STRIDE;
-        link = o; o += n_links * LSTATE * BWD_TILE;
-        slots = o; o += n_slots * 12 * BWD_TILE;
-        scratch = o; o += 25 * SCR_LD;
+        link = o; o += n_links * LSTATE * tile;
+        slots = o; o += n_slots * 12 * tile;
+        scratch = o; o += 25 * (tile + 1);
         acc = o; o += n_links * DRMB200_TABLE_STRIDE;
         total_floats = o;
     }
 };
 
-template <bool NEED_TABLE>
-__global__ void __launch_bounds__(BWD_TILE, 1)
+template <bool NEED_TABLE, int T>
+__global__ void __launch_bounds__(T)
 rnea_backward_kernel(const __grid_constant__ TreeProgram prog, const RneaBwdArgs args) {
     extern __shared__ __align__(128) float smem[];
     const int n = prog.n_dofs, N = prog.n_links;
-    const RneaBwdSmem L(n, N, prog.n_slots);
+    const RneaBwdSmem L(T, n, N, prog.n_slots);
     float* s_q = smem + L.q;
     float* s_qd = smem + L.qd;
     float* s_qdd = smem + L.qdd;
@@ -403,7 +405,6 @@ rnea_backward_kernel(const __grid_constant__ TreeProgram prog, const RneaBwdArgs
     float* s_acc = smem + L.acc;
     const int tid = threadIdx.x;
     const bool vec_ok = args.vec_ok;
-    constexpr int T = BWD_TILE;
     const float grav = (args.flags & DRMB200_GRAVITY) ? GRAVITY_B : 0.f;
     const bool damp = (args.flags & DRMB200_DAMPING) != 0;
 
@@ -522,7 +523,7 @@ rnea_backward_kernel(const __grid_constant__ TreeProgram prog, const RneaBwdArgs
                 float vals[13];
                 m3_to_array(Fbar, vals);
                 vals[9] = rbar.x; vals[10] = rbar.y; vals[11] = rbar.z; vals[12] = dbar;
-                block_accumulate<13>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active,
+                block_accumulate<13, T>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active,
                                      [](int j) { return j < 12 ? j : 25; });
             }
         }
@@ -618,7 +619,7 @@ rnea_backward_kernel(const __grid_constant__ TreeProgram prog, const RneaBwdArgs
                 if (c >= 0) rotate_z(Fbar, cs, -sn);
                 m3_to_array(Fbar, vals);
                 vals[9] = rbar.x; vals[10] = rbar.y; vals[11] = rbar.z;
-                block_accumulate<25>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active, [](int j) { return j; });
+                block_accumulate<25, T>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active, [](int j) { return j; });
             }
         }
         __syncthreads();
@@ -659,21 +660,22 @@ int inverse_dynamics_backward_device(const drmb200_topology_t* topo, const float
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.vec_ok = (al16(q) && al16(qd) && al16(qdd) && al16(g_tau) && al16(q_grad) && al16(qd_grad) && al16(qdd_grad)) ? 1 : 0;
 
-    const RneaBwdSmem L(prog.n_dofs, prog.n_links, prog.n_slots);
-    const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
+    int tile = 128;
+    while (tile > 32 && (size_t)RneaBwdSmem(tile, prog.n_dofs, prog.n_links, prog.n_slots).total_floats * sizeof(float) > BWD_SMEM_BUDGET) tile >>= 1;
+    const size_t smem_bytes = (size_t)RneaBwdSmem(tile, prog.n_dofs, prog.n_links, prog.n_slots).total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("rnea backward needs %zu B of shared memory per CTA (> 227 KB): model too large", smem_bytes); return DRMB200_ELIMIT; }
-    const int64_t tiles = (batch + BWD_TILE - 1) / BWD_TILE;
+    const int64_t tiles = (batch + tile - 1) / tile;
     int grid = 0;
     const bool need_table = table_grad != nullptr;
-    if (need_table) {
-        rc = persistent_grid(rnea_backward_kernel<true>, smem_bytes, tiles, &grid, "rnea backward");
-        if (rc != DRMB200_OK) return rc;
-        rnea_backward_kernel<true><<<grid, BWD_TILE, smem_bytes, stream>>>(prog, args);
-    } else {
-        rc = persistent_grid(rnea_backward_kernel<false>, smem_bytes, tiles, &grid, "rnea backward");
-        if (rc != DRMB200_OK) return rc;
-        rnea_backward_kernel<false><<<grid, BWD_TILE, smem_bytes, stream>>>(prog, args);
-    }
+#define DRM_LAUNCH_IDB(NT, TT)                                                                              \
+    do {                                                                                                    \
+        rc = persistent_grid(rnea_backward_kernel<NT, TT>, TT, smem_bytes, tiles, &grid, "rnea backward");  \
+        if (rc != DRMB200_OK) return rc;                                                                    \
+        rnea_backward_kernel<NT, TT><<<grid, TT, smem_bytes, stream>>>(prog, args);                         \
+    } while (0)
+    if (need_table) { if (tile == 128) DRM_LAUNCH_IDB(true, 128); else if (tile == 64) DRM_LAUNCH_IDB(true, 64); else DRM_LAUNCH_IDB(true, 32); }
+    else            { if (tile == 128) DRM_LAUNCH_IDB(false, 128); else if (tile == 64) DRM_LAUNCH_IDB(false, 64); else DRM_LAUNCH_IDB(false, 32); }
+#undef DRM_LAUNCH_IDB
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("rnea backward launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();

