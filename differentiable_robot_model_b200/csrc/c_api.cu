@@ -27,12 +27,15 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // Tuning knobs for A/B measurements, overridable with the environment or drmb200_set_option():
 //   0 "fk_variant" (DRMB200_FK_VARIANT): 1 = TMA bulk-copy staging (default), 0 = cooperative float4 copies
 //   1 "fk_tile"    (DRMB200_FK_TILE):    configurations per CTA, 64 / 128 / 256; 0 = pick by batch size
-//   2 "fk_unroll"  (DRMB200_FK_UNROLL):  1 = unrolled register-Jacobian kernel for paths <= 8 links (default), 0 = rolled
+//   2 "fk_unroll"  (DRMB200_FK_UNROLL):  0 = rolled chain walk (default), 1 = fully unrolled register-Jacobian
+//                  kernel for paths <= 8 links.  Measured (profiles/r01/v3_sweep_fk_variants.json): the unrolled
+//                  variant needs 80 registers and ~3x the code and is SLOWER (16.8 vs 20.6 G cfg/s at 65 536 x 4
+//                  in flight, 19.8 vs 21.0 at 2^22), so it is kept only as an A/B switch.
 int get_option(int which) {
     int v = g_options[which].load(std::memory_order_relaxed);
     if (v < 0) {
         static const char* names[3] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL"};
-        static const int defaults[3] = {1, 0, 1};
+        static const int defaults[3] = {1, 0, 0};
         const char* e = getenv(names[which]);
         v = e ? atoi(e) : defaults[which];
         g_options[which].store(v, std::memory_order_relaxed);

@@ -323,10 +323,12 @@ int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const fl
     args.aligned = (al16(q) && al16(pos) && al16(quat) && al16(jlin) && al16(jang)) ? 1 : 0;
     args.use_bulk = get_option(0) != 0;
 
-    // Tile size: small tiles give more CTAs (better SM fill for small batches and more resident warps
-    // per SM, since shared memory -- 32 n + 28 bytes per configuration -- is the occupancy limiter).
+    // Tile size, from the measured sweep (profiles/r01/v3_sweep_fk_variants.json, Kuka, rolled kernel):
+    //   2^22 per launch:   tile 64 -> 21.99 G cfg/s, 128 -> 20.96, 256 -> 16.66   (shared memory, 32 n + 28 bytes
+    //                      per configuration, is the occupancy limiter: smaller tiles pack SMs tighter)
+    //   65 536 per launch, 4 launches in flight: tile 128 -> 3.19 us, 64 -> 3.29 us, 256 -> 4.01 us
     int tile = get_option(1);
-    if (tile != 64 && tile != 128 && tile != 256) tile = (batch <= 148 * 1024) ? 64 : 128;
+    if (tile != 64 && tile != 128 && tile != 256) tile = (batch <= 148 * 1024) ? 128 : 64;
     const bool with_jac = jlin != nullptr;
     switch (prog.n_dofs) {
         case 2: return launch_fk_t<2>(tile, with_jac, prog, args, stream);

@@ -227,6 +227,58 @@ class DifferentiableRobotModel(torch.nn.Module):
         return self.compute_inverse_dynamics(q, qd, q.new_zeros(q.shape), include_gravity, use_damping)
 
     # ------------------------------------------------------------------------------------------
+    # callers of the hot path (SURVEY.md section 8f "next" rows) -- thin compositions of the RNEA / FK kernels
+    # ------------------------------------------------------------------------------------------
+    @tensor_check
+    def compute_lagrangian_inertia_matrix(
+        self,
+        q: torch.Tensor,
+        include_gravity: Optional[bool] = True,
+        use_damping: Optional[bool] = True,
+    ) -> torch.Tensor:
+        r"""Joint-space mass matrix ``H(q)`` ``[batch_size x n_dofs x n_dofs]``.  Same construction as the reference
+        (``robot_model.py:403-450``: column j = ID(q, 0, e_j) - ID(q, 0, 0)), but as ONE RNEA launch over a
+        ``(n_dofs + 1) x batch`` stacked batch instead of n+1 walks of the per-link op graph."""
+        assert q.shape[1] == self._n_dofs
+        B, n = q.shape
+        zero = q.new_zeros((n + 1) * B, n)
+        qdd = zero.clone().view(n + 1, B, n)
+        idx = torch.arange(n, device=q.device)
+        qdd[idx, :, idx] = 1.0                                  # slab j: unit acceleration of joint j; slab n: zero
+        tau = self.compute_inverse_dynamics(q.repeat(n + 1, 1), zero, qdd.view(-1, n), include_gravity, use_damping)
+        tau = tau.view(n + 1, B, n)
+        return (tau[:n] - tau[n:]).permute(1, 2, 0).contiguous()
+
+    @tensor_check
+    def compute_forward_dynamics(
+        self,
+        q: torch.Tensor,
+        qd: torch.Tensor,
+        f: torch.Tensor,
+        include_gravity: Optional[bool] = True,
+        use_damping: Optional[bool] = False,
+    ) -> torch.Tensor:
+        r"""Joint accelerations under applied torques ``f``: solves ``H(q) qdd = f - nle(q, qd)``.  The reference
+        evaluates the articulated-body algorithm (``robot_model.py:488-624``); both are exact solutions of the same
+        equations of motion (the reference's own tolerance against pybullet is rtol 1e-2).  Unlike the reference this
+        does not modify ``f`` in place when ``use_damping`` is set (``robot_model.py:521``)."""
+        self._check_q(q, qd, f)
+        nle = self.compute_inverse_dynamics(q, qd, torch.zeros_like(q), include_gravity, use_damping)
+        H = self.compute_lagrangian_inertia_matrix(q, include_gravity=False, use_damping=False)
+        return torch.linalg.solve(H, (f - nle).unsqueeze(2)).squeeze(2)
+
+    @tensor_check
+    def compute_forward_kinematics_all_links(self, q: torch.Tensor) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+        r"""``{link_name: (pos, quat)}`` for every link (``robot_model.py:198-221``), one FK launch per link.
+        Like the reference, 1-D inputs give un-squeezed ``[1, .]`` values (the dict bypasses the squeeze)."""
+        self._check_q(q)
+        out = {}
+        for name in self.get_link_names():
+            pos, quat, _, _ = self._fk_jacobian(q, name, True, True, False)
+            out[name] = (pos, quat)
+        return out
+
+    # ------------------------------------------------------------------------------------------
     # learnable link parameters (robot_model.py:669-713)
     # ------------------------------------------------------------------------------------------
     def _get_parent_object_of_param(self, link_name: str, parameter_name: str):

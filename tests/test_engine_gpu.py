@@ -31,11 +31,18 @@ def cuda(a):
     return torch.tensor(np.asarray(a), dtype=torch.float32, device=DEV)
 
 
-@pytest.fixture(params=[1, 0], ids=["tma_bulk", "coop_copy"])
+@pytest.fixture(params=[(1, 0, 0), (0, 0, 0), (1, 1, 64), (1, 0, 256)],
+                ids=["tma_bulk", "coop_copy", "unrolled_tile64", "tile256"])
 def fk_variant(request):
-    engine.set_option("fk_variant", request.param)
+    """Every staging / unrolling / tile variant of the FK kernel must give the same parity."""
+    variant, unroll, tile = request.param
+    engine.set_option("fk_variant", variant)
+    engine.set_option("fk_unroll", unroll)
+    engine.set_option("fk_tile", tile)
     yield request.param
     engine.set_option("fk_variant", 1)
+    engine.set_option("fk_unroll", 0)
+    engine.set_option("fk_tile", 0)
 
 
 # ------------------------------------------------------------------------------------------------
