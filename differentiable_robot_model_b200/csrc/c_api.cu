@@ -55,6 +55,8 @@ int inverse_dynamics_backward_device(const drmb200_topology_t*, const float*, co
                                      const float*, int64_t, uint32_t, const float*, float*, float*, float*,
                                      float*, void*, cudaStream_t);
 int64_t table_grad_workspace_bytes(const drmb200_topology_t*, int64_t);
+int build_table_device(const float*, int32_t, float*, cudaStream_t);
+int build_table_backward_device(const float*, const float*, int32_t, float*, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // host-buffer pipeline for FK + Jacobian
@@ -197,6 +199,15 @@ int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo, const floa
     return drm::inverse_dynamics_backward_device(topo, table, q, qd, qdd, batch, flags, g_tau, q_grad, qd_grad,
                                                  qdd_grad, table_grad, workspace,
                                                  static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_build_link_table(const float* raw, int32_t n_links, float* table, void* cuda_stream) {
+    return drm::build_table_device(raw, n_links, table, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_build_link_table_backward(const float* raw, const float* table_grad, int32_t n_links, float* raw_grad,
+                                      void* cuda_stream) {
+    return drm::build_table_backward_device(raw, table_grad, n_links, raw_grad, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int drmb200_fk_jacobian_host(const drmb200_topology_t* topo, int32_t ee_link, int32_t device, const float* table,

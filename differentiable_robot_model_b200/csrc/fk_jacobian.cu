@@ -159,23 +159,40 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
                 }
             }
         } else {
-            for (int k = 0; k < len; ++k) {
-                V3 z, m;
+            // explicit shared-window addresses (see smem_addr_opaque): table cursor, this thread's q / J rows
+            uint32_t a_tab = smem_addr_opaque(s_tab);
+            const uint32_t a_q = smem_addr_opaque(qrow);
+            const uint32_t a_jl = smem_addr_opaque(jl), a_ja = smem_addr_opaque(ja);
+            const uint32_t n4 = 4u * n;
+            for (int k = 0; k < len; ++k, a_tab += 48) {
+                M3 F; V3 r;
+                load_Fr_s(a_tab, F, r);
+                p = mul_add(R, r, p);            // p_i = R_parent r_i + p_parent
+                R = mul(R, F);                   // R_parent F~_i
                 const int c = prog.dof[k];
-                walk_link<false, WITH_JAC>(s_tab + k * 12, qrow, c, R, p, z, m);
-                if (WITH_JAC && c >= 0) {
-                    ja[c] = z.x; ja[n + c] = z.y; ja[2 * n + c] = z.z;
-                    jl[c] = m.x; jl[n + c] = m.y; jl[2 * n + c] = m.z;
+                if (c >= 0) {
+                    float sn, cs;
+                    sincos_pi2(lds_f32(a_q + 4u * c), sn, cs);
+                    if (WITH_JAC) {
+                        const V3 z = col2(R);    // joint axis in the world frame (unchanged by Rz)
+                        const V3 m = cross(z, p);
+                        const uint32_t o = 4u * c;
+                        sts_f32(a_ja + o, z.x); sts_f32(a_ja + o + n4, z.y); sts_f32(a_ja + o + 2 * n4, z.z);
+                        sts_f32(a_jl + o, m.x); sts_f32(a_jl + o + n4, m.y); sts_f32(a_jl + o + 2 * n4, m.z);
+                    }
+                    rotate_z(R, cs, sn);
                 }
             }
             if (WITH_JAC) {
+                // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
                 for (int k = 0; k < len; ++k) {
                     const int c = prog.dof[k];
                     if (c < 0) continue;
-                    const V3 z = v3(ja[c], ja[n + c], ja[2 * n + c]);
-                    const V3 m = v3(jl[c], jl[n + c], jl[2 * n + c]);
+                    const uint32_t o = 4u * c;
+                    const V3 z = v3(lds_f32(a_ja + o), lds_f32(a_ja + o + n4), lds_f32(a_ja + o + 2 * n4));
+                    const V3 m = v3(lds_f32(a_jl + o), lds_f32(a_jl + o + n4), lds_f32(a_jl + o + 2 * n4));
                     const V3 j = cross_add(z, p, v3(-m.x, -m.y, -m.z));
-                    jl[c] = j.x; jl[n + c] = j.y; jl[2 * n + c] = j.z;
+                    sts_f32(a_jl + o, j.x); sts_f32(a_jl + o + n4, j.y); sts_f32(a_jl + o + 2 * n4, j.z);
                 }
             }
         }

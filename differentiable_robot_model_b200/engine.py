@@ -43,6 +43,9 @@ _SIGNATURES = {
                                                          _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                          _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "drmb200_build_link_table": (ctypes.c_int, [_c_float_p, ctypes.c_int32, _c_float_p, ctypes.c_void_p]),
+    "drmb200_build_link_table_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int32, _c_float_p,
+                                                         ctypes.c_void_p]),
     "drmb200_fk_jacobian_host": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, ctypes.c_int32, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p]),
@@ -162,6 +165,34 @@ def _workspace(topo, batch, device):
 # ------------------------------------------------------------------------------------------------
 # autograd
 # ------------------------------------------------------------------------------------------------
+class BuildLinkTableFunction(torch.autograd.Function):
+    """raw link parameters [n_links, 20] -> link table [n_links, 28] (csrc/table.cu), one launch each way."""
+
+    @staticmethod
+    def forward(ctx, raw):
+        _require_cuda(raw)
+        raw = raw.contiguous()
+        n_links = raw.shape[0]
+        table = torch.empty((n_links, 28), device=raw.device, dtype=torch.float32)
+        with torch.cuda.device(raw.device):
+            rc = lib().drmb200_build_link_table(_ptr(raw), n_links, _ptr(table), _stream())
+        _check(rc, "drmb200_build_link_table")
+        ctx.save_for_backward(raw)
+        return table
+
+    @staticmethod
+    def backward(ctx, g_table):
+        (raw,) = ctx.saved_tensors
+        g_table = g_table.contiguous()
+        _require_cuda(g_table)
+        g_raw = torch.empty_like(raw)
+        with torch.cuda.device(raw.device):
+            rc = lib().drmb200_build_link_table_backward(_ptr(raw), _ptr(g_table), raw.shape[0], _ptr(g_raw), _stream())
+        _check(rc, "drmb200_build_link_table_backward")
+        return g_raw
+
+
+
 class FkJacobianFunction(torch.autograd.Function):
     """(table, q) -> (pos, quat, jac_lin, jac_ang); analytic backward kernel."""
 

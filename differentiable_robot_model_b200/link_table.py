@@ -93,8 +93,33 @@ def _rpy_to_matrix(rpy):
     return torch.stack(rows, dim=1)          # [N, 9] row-major
 
 
+def gather_raw_parameters(bodies, device):
+    """``[n_links, 20]`` = rpy(3) | trans(3) | mass | com(3) | inertia_mat(9) | damping per link: ONE ``torch.cat``
+    over whatever the per-link parameter callables return (differentiable w.r.t. learnable modules)."""
+    f32 = dict(dtype=torch.float32, device=device)
+    zero = torch.zeros(1, **f32)
+    pieces = []
+    for body in bodies:
+        movable = body.joint_idx is not None
+        # fixed joints keep their construction-time origin (reference quirk, rigid_body.py:64-67)
+        pieces.append((body.rot_angles() if movable else body._ctor_rot_angles).reshape(3))
+        pieces.append((body.trans() if movable else body._ctor_trans).reshape(3))
+        m, c, inert = body.inertia._get_parameter_values()
+        pieces += [m.reshape(1), c.reshape(3), inert.reshape(9)]
+        d = body.joint_damping() if movable else None
+        pieces.append(d.reshape(1) if d is not None else zero)
+    return torch.cat([p.to(**f32) for p in pieces]).reshape(len(bodies), 20)
+
+
 def build_link_table(bodies, device):
-    """Evaluate every link's parameter callables into the ``[n_links, 28]`` fp32 device table."""
+    """Evaluate every link's parameter callables into the ``[n_links, 28]`` fp32 device table.
+
+    On a CUDA device: one ``torch.cat`` + one kernel (``engine.BuildLinkTableFunction`` -> ``csrc/table.cu``), with an
+    analytic backward kernel.  On the CPU (host-side introspection / tests only; compute entry points refuse CPU
+    tensors) the same table is assembled with batched torch ops below."""
+    if torch.device(device).type == "cuda":
+        from . import engine
+        return engine.BuildLinkTableFunction.apply(gather_raw_parameters(bodies, device))
     f32 = dict(dtype=torch.float32, device=device)
     trans, rpy, mass, com, inertia, damping = [], [], [], [], [], []
     for i, body in enumerate(bodies):

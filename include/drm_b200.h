@@ -128,6 +128,20 @@ int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo,
                                       float* table_grad, void* workspace, void* cuda_stream);
 
 /*
+ * Link-parameter rows -> link table, and its adjoint (device pointers, asynchronous).
+ *   raw       [n_links, DRMB200_RAW_STRIDE]: rpy(3) | trans(3) | mass | com(3) | inertia_mat(9, at the COM) | damping
+ *             -- the values the reference keeps in per-link modules (rigid_body.py:47-49,
+ *             spatial_vector_algebra.py:312-314); for fixed joints pass the construction-time origin.
+ *   table     [n_links, 28] as documented above (F = Rz Ry Rx, Io = I_c + m S(c)S(c)^T, mc = m c).
+ * The backward maps table_grad [n_links, 28] to raw_grad [n_links, 20].  These replace ~60 small torch ops
+ * (and ~100 autograd nodes) per call when link parameters are being learned.
+ */
+#define DRMB200_RAW_STRIDE 20
+int drmb200_build_link_table(const float* raw, int32_t n_links, float* table, void* cuda_stream);
+int drmb200_build_link_table_backward(const float* raw, const float* table_grad, int32_t n_links,
+                                      float* raw_grad, void* cuda_stream);
+
+/*
  * Host-buffer variant of drmb200_fk_jacobian: q and the outputs are HOST pointers (pinned memory
  * gives full PCIe bandwidth; pageable memory works).  `table` is still a device pointer (it is
  * < 8 KB and lives with the model).  The call splits the batch into chunks, overlaps
