@@ -390,7 +390,7 @@ def main():
 
     if rank == 0:
         result["clocks"] = sampler.summary()
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:         # reported at N = 1 only
             times = time_cpu_port(BATCH, 10.0, 200)
             cores = _CPU_THREADS
             v = BATCH * len(times) / sum(times)

@@ -345,7 +345,9 @@ int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const fl
     //                      per configuration, is the occupancy limiter: smaller tiles pack SMs tighter)
     //   65 536 per launch, 4 launches in flight: tile 128 -> 3.19 us, 64 -> 3.29 us, 256 -> 4.01 us
     int tile = get_option(1);
-    if (tile != 64 && tile != 128 && tile != 256) tile = (batch <= 148 * 1024) ? 128 : 64;
+    //   16-DoF Allegro hand, 2^21 per launch: tile 128 -> 9.8 G cfg/s, tile 64 -> 7.0 (even row strides: 16-way
+    //                      bank conflicts hurt the narrower tile more), so wide rows keep 128
+    if (tile != 64 && tile != 128 && tile != 256) tile = (batch <= 148 * 1024 || prog.n_dofs > 8) ? 128 : 64;
     const bool with_jac = jlin != nullptr;
     switch (prog.n_dofs) {
         case 2: return launch_fk_t<2>(tile, with_jac, prog, args, stream);

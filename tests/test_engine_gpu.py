@@ -52,6 +52,7 @@ def test_fk_jacobian_matches_reference_golden(robot_stem, fk_variant):
     g = load_golden(robot_stem)
     m = gpu_model(robot_stem)
     q = cuda(g["q"])
+    m._link_table()                                  # constant model: built once (one launch), then cached
     launches = engine.launch_count()
     for link in g["fk_links"].tolist():
         pos, quat = m.compute_forward_kinematics(q, link)
