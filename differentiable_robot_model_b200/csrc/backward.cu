@@ -322,8 +322,12 @@ int fk_jacobian_backward_device(const drmb200_topology_t* topo, int32_t ee_link,
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.vec_ok = (al16(q) && al16(g_pos) && al16(g_quat) && al16(g_jl) && al16(g_ja) && al16(q_grad)) ? 1 : 0;
 
-    int tile = 128;
-    while (tile > 32 && (size_t)FkBwdSmem(tile, prog.n_dofs, prog.len).total_floats * sizeof(float) > BWD_SMEM_BUDGET) tile >>= 1;
+    int tile = 32, best_warps = 0;           // the tile that keeps the most warps resident per SM
+    for (int t = 128; t >= 32; t >>= 1) {
+        const size_t b = (size_t)FkBwdSmem(t, prog.n_dofs, prog.len).total_floats * sizeof(float) + 1024;
+        const int warps = b > 227 * 1024 ? 0 : (int)((227 * 1024) / b) * (t / 32);
+        if (warps > best_warps) { best_warps = warps; tile = t; }
+    }
     const size_t smem_bytes = (size_t)FkBwdSmem(tile, prog.n_dofs, prog.len).total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("fk backward needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
     const int64_t tiles = (batch + tile - 1) / tile;
@@ -660,8 +664,14 @@ int inverse_dynamics_backward_device(const drmb200_topology_t* topo, const float
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.vec_ok = (al16(q) && al16(qd) && al16(qdd) && al16(g_tau) && al16(q_grad) && al16(qd_grad) && al16(qdd_grad)) ? 1 : 0;
 
-    int tile = 128;
-    while (tile > 32 && (size_t)RneaBwdSmem(tile, prog.n_dofs, prog.n_links, prog.n_slots).total_floats * sizeof(float) > BWD_SMEM_BUDGET) tile >>= 1;
+    // shared memory (20 floats per link per configuration) is the occupancy limiter: pick the tile that keeps the
+    // most warps resident per SM (Kuka: 128 -> 1 CTA = 4 warps, 64 -> 3 CTAs = 6 warps), larger tile on ties
+    int tile = 32, best_warps = 0;
+    for (int t = 128; t >= 32; t >>= 1) {
+        const size_t b = (size_t)RneaBwdSmem(t, prog.n_dofs, prog.n_links, prog.n_slots).total_floats * sizeof(float) + 1024;
+        const int warps = b > 227 * 1024 ? 0 : (int)((227 * 1024) / b) * (t / 32);
+        if (warps > best_warps) { best_warps = warps; tile = t; }
+    }
     const size_t smem_bytes = (size_t)RneaBwdSmem(tile, prog.n_dofs, prog.n_links, prog.n_slots).total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("rnea backward needs %zu B of shared memory per CTA (> 227 KB): model too large", smem_bytes); return DRMB200_ELIMIT; }
     const int64_t tiles = (batch + tile - 1) / tile;

@@ -115,32 +115,45 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
     if (bulk) mbar_wait(&mbar, 0);
 
     if (tid < valid) {
-        const float* qrow = s_q + tid * n;
-        const float* qdrow = s_qd + tid * n;
-        const float* qddrow = s_qdd + tid * n;
-        float* taurow = s_tau + tid * n;
+        // explicit 32-bit shared-window addresses (see smem_addr_opaque in drm_common.cuh)
+        const uint32_t a_q = smem_addr_opaque(s_q + tid * n), a_qd = smem_addr_opaque(s_qd + tid * n);
+        const uint32_t a_qdd = smem_addr_opaque(s_qdd + tid * n), a_tau = smem_addr_opaque(s_tau + tid * n);
+        const uint32_t a_tab = smem_addr_opaque(s_tab);
+        const uint32_t a_link = smem_addr_opaque(s_link + tid), a_slot = smem_addr_opaque(s_slot + tid);
+        constexpr uint32_t E = 4u * T;                      // byte stride between elements of a slot-major vector
+        auto ldv_s = [](uint32_t a) { return v3(lds_f32(a), lds_f32(a + E), lds_f32(a + 2 * E)); };
+        auto stv_s = [](uint32_t a, V3 x) { sts_f32(a, x.x); sts_f32(a + E, x.y); sts_f32(a + 2 * E, x.z); };
         const float g = (args.flags & DRMB200_GRAVITY) ? GRAVITY : 0.f;
         const bool damp = (args.flags & DRMB200_DAMPING) != 0;
 
         // ---- pass 1: root -> leaves, motion state + body wrench ------------------------------------
         V3 w = v3(0.f, 0.f, 0.f), v = w, al = w, a = w;     // state of the previously processed link
         for (int i = 1; i < N; ++i) {
-            const LinkRow C = load_row(s_tab + i * DRMB200_TABLE_STRIDE);
+            const uint32_t row = a_tab + i * (DRMB200_TABLE_STRIDE * 4);
+            LinkRow C;
+            load_Fr_s(row, C.F, C.r);
+            {
+                const float4 d = lds_f32x4(row + 48), e = lds_f32x4(row + 64), f = lds_f32x4(row + 80), gg = lds_f32x4(row + 96);
+                C.Io.a00 = d.x; C.Io.a01 = d.y; C.Io.a02 = d.z; C.Io.a10 = d.w; C.Io.a11 = e.x; C.Io.a12 = e.y;
+                C.Io.a20 = e.z; C.Io.a21 = e.w; C.Io.a22 = f.x;
+                C.mc = v3(f.y, f.z, f.w);
+                C.m = gg.x; C.d = gg.y;
+            }
             const int src = prog.psrc[i];
             V3 wp, vp, alp, ap;
             if (src == 0) { wp = w; vp = v; alp = al; ap = a; }
             else if (src < 0) { wp = vp = alp = v3(0.f, 0.f, 0.f); ap = v3(0.f, 0.f, g); }
             else {
-                const float* sl = s_slot + (src - 1) * 12 * T + tid;
-                wp = ldv(sl, T); vp = ldv(sl + 3 * T, T); alp = ldv(sl + 6 * T, T); ap = ldv(sl + 9 * T, T);
+                const uint32_t sl = a_slot + (src - 1) * 12 * E;
+                wp = ldv_s(sl); vp = ldv_s(sl + 3 * E); alp = ldv_s(sl + 6 * E); ap = ldv_s(sl + 9 * E);
             }
             M3 M = C.F;
             const int c = prog.dof[i];
             float cs = 1.f, sn = 0.f, qd_k = 0.f, qdd_k = 0.f;
             if (c >= 0) {
-                qd_k = qdrow[c];
-                qdd_k = qddrow[c];
-                sincos_pi2(qrow[c], sn, cs);
+                qd_k = lds_f32(a_qd + 4u * c);
+                qdd_k = lds_f32(a_qdd + 4u * c);
+                sincos_pi2(lds_f32(a_q + 4u * c), sn, cs);
                 rotate_z(M, cs, sn);
             }
             // velocities (robot_model.py:183-193), accelerations (robot_model.py:269-277)
@@ -155,37 +168,38 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
             const V3 ha_v = mul_add(C.Io, w, cross(C.mc, v));
             const V3 f = cross_add(w, hl_v, hl_a);
             const V3 nn = cross_add(w, ha_v, cross_add(v, hl_v, ha_a));
-            float* lk = s_link + i * 8 * T + tid;
-            stv(lk, T, f); stv(lk + 3 * T, T, nn);
-            lk[6 * T] = cs; lk[7 * T] = sn;
+            const uint32_t lk = a_link + i * 8 * E;
+            stv_s(lk, f); stv_s(lk + 3 * E, nn);
+            sts_f32(lk + 6 * E, cs); sts_f32(lk + 7 * E, sn);
             const int sv = prog.save[i];
             if (sv >= 0) {
-                float* sl = s_slot + sv * 12 * T + tid;
-                stv(sl, T, w); stv(sl + 3 * T, T, v); stv(sl + 6 * T, T, al); stv(sl + 9 * T, T, a);
+                const uint32_t sl = a_slot + sv * 12 * E;
+                stv_s(sl, w); stv_s(sl + 3 * E, v); stv_s(sl + 6 * E, al); stv_s(sl + 9 * E, a);
             }
         }
 
         // ---- pass 2: leaves -> root, wrench propagation + joint torques (robot_model.py:284-301, 353-373)
         for (int i = N - 1; i >= 1; --i) {
-            const float* lk = s_link + i * 8 * T + tid;
-            const V3 f = ldv(lk, T);
-            const V3 nn = ldv(lk + 3 * T, T);
+            const uint32_t lk = a_link + i * 8 * E;
+            const V3 f = ldv_s(lk);
+            const V3 nn = ldv_s(lk + 3 * E);
             const int c = prog.dof[i];
+            const uint32_t row = a_tab + i * (DRMB200_TABLE_STRIDE * 4);
             if (c >= 0) {
                 float t = nn.z;
-                if (damp) t = fmaf(s_tab[i * DRMB200_TABLE_STRIDE + 25], qdrow[c], t);
-                taurow[c] = t;
+                if (damp) t = fmaf(lds_f32(row + 100), lds_f32(a_qd + 4u * c), t);
+                sts_f32(a_tau + 4u * c, t);
             }
             const int p = prog.parent[i];
             if (p > 0) {
                 M3 F; V3 r;
-                load_Fr(s_tab + i * DRMB200_TABLE_STRIDE, F, r);
-                const float cs = lk[6 * T], sn = lk[7 * T];
+                load_Fr_s(row, F, r);
+                const float cs = lds_f32(lk + 6 * E), sn = lds_f32(lk + 7 * E);
                 const V3 fp = mul(F, rotz(f, cs, sn));              // M f = F~ (Rz f)  (sva:281-291)
                 const V3 np = cross_add(r, fp, mul(F, rotz(nn, cs, sn)));
-                float* pk = s_link + p * 8 * T + tid;
-                pk[0] += fp.x; pk[T] += fp.y; pk[2 * T] += fp.z;
-                pk[3 * T] += np.x; pk[4 * T] += np.y; pk[5 * T] += np.z;
+                const uint32_t pk = a_link + p * 8 * E;
+                stv_s(pk, ldv_s(pk) + fp);
+                stv_s(pk + 3 * E, ldv_s(pk + 3 * E) + np);
             }
         }
     }
