@@ -27,15 +27,17 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 // Tuning knobs for A/B measurements, overridable with the environment or drmb200_set_option():
 //   0 "fk_variant" (DRMB200_FK_VARIANT): 1 = TMA bulk-copy staging (default), 0 = cooperative float4 copies
 //   1 "fk_tile"    (DRMB200_FK_TILE):    configurations per CTA, 64 / 128 / 256; 0 = pick by batch size
-//   2 "fk_unroll"  (DRMB200_FK_UNROLL):  0 = rolled chain walk (default), 1 = fully unrolled register-Jacobian
-//                  kernel for paths <= 8 links.  Measured (profiles/r01/v3_sweep_fk_variants.json): the unrolled
-//                  variant needs 80 registers and ~3x the code and is SLOWER (16.8 vs 20.6 G cfg/s at 65 536 x 4
-//                  in flight, 19.8 vs 21.0 at 2^22), so it is kept only as an A/B switch.
+//   2 "fk_unroll"  (DRMB200_FK_UNROLL):  0 = rolled chain walk, 1 = fully unrolled register-Jacobian kernel for
+//                  paths <= 8 links, 2 = auto (default): unrolled only for even n_dofs.  Measured
+//                  (profiles/r01/v3_sweep_fk_variants.json, v5_bench_other_configs.json): for the 7-DoF Kuka the
+//                  unrolled variant (80 registers, ~3x the code) is SLOWER (16.8 vs 20.6 G cfg/s at 65 536 x 4 in
+//                  flight, 19.8 vs 21.0 at 2^22); for the 16-DoF Allegro hand, whose even row strides make every J-tile
+//                  access a 16-way bank conflict, touching the tile once per column wins (9.8 vs 6.3 G cfg/s).
 int get_option(int which) {
     int v = g_options[which].load(std::memory_order_relaxed);
     if (v < 0) {
         static const char* names[3] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL"};
-        static const int defaults[3] = {1, 0, 0};
+        static const int defaults[3] = {1, 0, 2};
         const char* e = getenv(names[which]);
         v = e ? atoi(e) : defaults[which];
         g_options[which].store(v, std::memory_order_relaxed);
@@ -56,6 +58,8 @@ int inverse_dynamics_backward_device(const drmb200_topology_t*, const float*, co
                                      float*, void*, cudaStream_t);
 int64_t table_grad_workspace_bytes(const drmb200_topology_t*, int64_t);
 int build_table_device(const float*, int32_t, float*, cudaStream_t);
+int kinematic_state_device(const drmb200_topology_t*, const float*, const float*, const float*, int64_t, float*, float*,
+                           float*, cudaStream_t);
 int build_table_backward_device(const float*, const float*, int32_t, float*, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
@@ -199,6 +203,11 @@ int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo, const floa
     return drm::inverse_dynamics_backward_device(topo, table, q, qd, qdd, batch, flags, g_tau, q_grad, qd_grad,
                                                  qdd_grad, table_grad, workspace,
                                                  static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_kinematic_state(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                            int64_t batch, float* poses, float* quats, float* vels, void* cuda_stream) {
+    return drm::kinematic_state_device(topo, table, q, qd, batch, poses, quats, vels, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int drmb200_build_link_table(const float* raw, int32_t n_links, float* table, void* cuda_stream) {

@@ -307,7 +307,11 @@ static int launch_fk(const PathProgram& prog, const FkArgs& args, cudaStream_t s
 
 template <int NDOF, int TILE, bool WITH_JAC>
 static int launch_fk_l(const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {
-    const bool unrolled = prog.len <= 8 && get_option(2) != 0;
+    // Rolled vs unrolled (measured, profiles/r01): for odd n (Kuka, 7) the rolled kernel wins (21.9 vs 19.8 G cfg/s).
+    // For even n the per-thread J rows have even strides -> 16-way bank conflicts on every J access; the unrolled
+    // kernel touches the J tile once per column instead of three times and wins (Allegro, n = 16: 9.8 vs 6.3 G cfg/s).
+    const int opt = get_option(2);                     // 0 rolled, 1 unrolled, 2 auto
+    const bool unrolled = prog.len <= 8 && (opt == 1 || (opt != 0 && (prog.n_dofs % 2) == 0));
     return unrolled ? launch_fk<NDOF, TILE, WITH_JAC, 8>(prog, args, stream)
                     : launch_fk<NDOF, TILE, WITH_JAC, 0>(prog, args, stream);
 }

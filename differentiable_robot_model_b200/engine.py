@@ -43,6 +43,8 @@ _SIGNATURES = {
                                                          _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                          _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "drmb200_kinematic_state": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, ctypes.c_int64,
+                                               _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "drmb200_build_link_table": (ctypes.c_int, [_c_float_p, ctypes.c_int32, _c_float_p, ctypes.c_void_p]),
     "drmb200_build_link_table_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int32, _c_float_p,
                                                          ctypes.c_void_p]),
@@ -146,6 +148,22 @@ def inverse_dynamics_raw(topo, table, q, qd, qdd, flags, out=None):
                                             flags, _ptr(tau), _stream())
     _check(rc, "drmb200_inverse_dynamics")
     return tau
+
+
+def kinematic_state_raw(topo, table, q, qd=None, want_poses=True, want_quats=False):
+    """Poses [N,12,B] (+ quaternions [N,4,B], + velocities [N,6,B] when qd is given) of every link, one launch."""
+    _require_cuda(table, q, qd)
+    q = q.contiguous()
+    qd = None if qd is None else qd.contiguous()
+    B, N, dev = q.shape[0], topo.n_links, q.device
+    poses = torch.empty((N, 12, B), device=dev, dtype=torch.float32) if want_poses else None
+    quats = torch.empty((N, 4, B), device=dev, dtype=torch.float32) if want_quats else None
+    vels = torch.empty((N, 6, B), device=dev, dtype=torch.float32) if qd is not None else None
+    with torch.cuda.device(dev):
+        rc = lib().drmb200_kinematic_state(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), B, _ptr(poses), _ptr(quats),
+                                           _ptr(vels), _stream())
+    _check(rc, "drmb200_kinematic_state")
+    return poses, quats, vels
 
 
 def fk_jacobian_host(topo, ee_link, device_index, table, q_host, pos, quat, jlin, jang):

@@ -93,22 +93,57 @@ def _rpy_to_matrix(rpy):
     return torch.stack(rows, dim=1)          # [N, 9] row-major
 
 
-def gather_raw_parameters(bodies, device):
-    """``[n_links, 20]`` = rpy(3) | trans(3) | mass | com(3) | inertia_mat(9) | damping per link: ONE ``torch.cat``
-    over whatever the per-link parameter callables return (differentiable w.r.t. learnable modules)."""
+RAW_STRIDE = 20       # DRMB200_RAW_STRIDE
+# (owner attribute, parameter name, offset in the raw row, size); trans / rot_angles / damping of FIXED joints are
+# frozen at their construction-time values (reference quirk, rigid_body.py:64-67)
+_RAW_FIELDS = (("body", "rot_angles", 0, 3), ("body", "trans", 3, 3), ("inertia", "mass", 6, 1),
+               ("inertia", "com", 7, 3), ("inertia", "inertia_mat", 10, 9), ("body", "joint_damping", 19, 1))
+
+
+def _raw_layout(bodies, device):
+    """Constant part of the raw block + where the learnable modules' outputs go.  Link parameters that are plain
+    constants (lambdas over the URDF tensors) are evaluated once; only ``torch.nn.Module`` parametrisations are
+    re-evaluated per call.  Cached per (ModuleList, set of learnable modules)."""
     f32 = dict(dtype=torch.float32, device=device)
-    zero = torch.zeros(1, **f32)
-    pieces = []
-    for body in bodies:
+    learnable, const_rows = [], []
+    for i, body in enumerate(bodies):
         movable = body.joint_idx is not None
-        # fixed joints keep their construction-time origin (reference quirk, rigid_body.py:64-67)
-        pieces.append((body.rot_angles() if movable else body._ctor_rot_angles).reshape(3))
-        pieces.append((body.trans() if movable else body._ctor_trans).reshape(3))
-        m, c, inert = body.inertia._get_parameter_values()
-        pieces += [m.reshape(1), c.reshape(3), inert.reshape(9)]
-        d = body.joint_damping() if movable else None
-        pieces.append(d.reshape(1) if d is not None else zero)
-    return torch.cat([p.to(**f32) for p in pieces]).reshape(len(bodies), 20)
+        row = torch.zeros(RAW_STRIDE, **f32)
+        for owner_name, pname, off, size in _RAW_FIELDS:
+            owner = body if owner_name == "body" else body.inertia
+            if owner_name == "body" and not movable:
+                if pname == "rot_angles":
+                    row[off:off + size] = body._ctor_rot_angles.reshape(3).to(**f32)
+                elif pname == "trans":
+                    row[off:off + size] = body._ctor_trans.reshape(3).to(**f32)
+                continue                                      # damping of a fixed joint stays 0
+            attr = getattr(owner, pname)
+            if isinstance(attr, torch.nn.Module):
+                learnable.append((attr, i * RAW_STRIDE + off, size))
+            else:
+                val = attr()
+                if val is not None:
+                    row[off:off + size] = val.detach().reshape(size).to(**f32)
+        const_rows.append(row)
+    const = torch.stack(const_rows).reshape(-1)
+    index = torch.tensor([o + k for _, o, s in learnable for k in range(s)], dtype=torch.long, device=device)
+    return const, learnable, index
+
+
+def gather_raw_parameters(bodies, device):
+    """``[n_links, 20]`` = rpy(3) | trans(3) | mass | com(3) | inertia_mat(9) | damping per link, differentiable
+    w.r.t. the learnable parametrisation modules: one ``torch.cat`` of their outputs + one ``index_copy`` into the
+    cached constant block (two launches, independent of the number of links)."""
+    sig = (str(device),) + tuple(id(getattr(b if o == "body" else b.inertia, p)) for b in bodies for o, p, _, _ in _RAW_FIELDS)
+    cached = getattr(bodies, "_drm_gather_cache", None)
+    if cached is None or cached[0] != sig:
+        cached = (sig,) + _raw_layout(bodies, device)
+        object.__setattr__(bodies, "_drm_gather_cache", cached)        # plain attribute on the ModuleList
+    _, const, learnable, index = cached
+    if not learnable:
+        return const.reshape(len(bodies), RAW_STRIDE)
+    vals = torch.cat([m().reshape(s).to(dtype=torch.float32, device=device) for m, _, s in learnable])
+    return const.index_copy(0, index, vals).reshape(len(bodies), RAW_STRIDE)
 
 
 def build_link_table(bodies, device):

@@ -68,6 +68,21 @@ class DifferentiableRigidBody(torch.nn.Module):
     def add_child(self, link: "DifferentiableRigidBody"):
         self._children.append(link)
 
+    # per-link kinematic state left behind by model.update_kinematic_state (reference: rigid_body.py:70-73)
+    def _bind_model(self, model):
+        import weakref
+        object.__setattr__(self, "_model_ref", weakref.ref(model))
+
+    @property
+    def pose(self):
+        """World pose of this link (``CoordinateTransform``) for the last ``update_kinematic_state`` call."""
+        return self._model_ref()._body_pose(self.joint_id)
+
+    @property
+    def vel(self):
+        """Body-frame spatial velocity (``SpatialMotionVec``) for the last ``update_kinematic_state`` call."""
+        return self._model_ref()._body_vel(self.joint_id)
+
     def get_joint_limits(self):
         return self.joint_limits
 

@@ -21,6 +21,7 @@ Deliberate deviations from the reference:
     reference's recursive variant depends on stale per-body state (``rigid_body.py:119``);
   * joint axes must be signed coordinate axes (true for every shipped URDF).
 """
+import contextlib
 import os
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Tuple
@@ -115,16 +116,35 @@ class DifferentiableRobotModel(torch.nn.Module):
             body.set_parent(self._bodies[parent_idx])
             self._bodies[parent_idx].add_child(body)
 
+        for body in self._bodies:
+            body._bind_model(self)
         self._topology = compile_topology(self._bodies, self._parent_idx)
+        self._kin_state = None
         self._table_cache = None
         self._table_cache_key = None
 
     # ------------------------------------------------------------------------------------------
     # link table
     # ------------------------------------------------------------------------------------------
+    @contextlib.contextmanager
+    def shared_link_table(self):
+        """Opt-in: every compute call inside the block uses ONE (differentiable) link table, built on entry.
+
+        By default each call of a model with learnable link parameters rebuilds the table, exactly like each call of
+        the reference rebuilds its per-link graph, so that separate ``backward()`` calls stay independent.  A training
+        step that evaluates several quantities before a single ``backward()`` (e.g. FK + Jacobian + inverse dynamics,
+        BASELINE config 5) can share the table and save the repeated parametrisation -> table work."""
+        self._shared_table = self._link_table()
+        try:
+            yield self._shared_table
+        finally:
+            self._shared_table = None
+
     def _link_table(self) -> torch.Tensor:
         """The ``[n_links, 28]`` device table.  Constant models build it once; with learnable link
         parameters it is rebuilt (differentiably) whenever a parameter changed or a graph is needed."""
+        if getattr(self, "_shared_table", None) is not None:
+            return self._shared_table
         params = list(self.parameters())
         needs_graph = torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if needs_graph:
@@ -268,15 +288,47 @@ class DifferentiableRobotModel(torch.nn.Module):
         return torch.linalg.solve(H, (f - nle).unsqueeze(2)).squeeze(2)
 
     @tensor_check
+    def update_kinematic_state(self, q: torch.Tensor, qd: torch.Tensor) -> None:
+        r"""World pose and body-frame spatial velocity of every link for joint state ``(q, qd)``
+        (``robot_model.py:140-195``), in ONE launch (``csrc/kinematic_state.cu``).  Afterwards
+        ``model._bodies[i].pose`` (a ``CoordinateTransform``) and ``model._bodies[i].vel`` (a ``SpatialMotionVec``)
+        are available like in the reference; they are views of the kernel's link-major output, built on access.
+        This state is NOT differentiable and is only refreshed by this method (the fused FK / RNEA kernels do not
+        write per-link state to HBM)."""
+        self._check_q(q, qd)
+        with torch.no_grad():
+            poses, _, vels = engine.kinematic_state_raw(self._topology, self._link_table().detach(), q, qd)
+        self._kin_state = (poses, vels)
+        return
+
+    def _body_pose(self, i):
+        from .spatial_vector_algebra import CoordinateTransform
+        state = getattr(self, "_kin_state", None)
+        if state is None:
+            raise RuntimeError("no kinematic state: call update_kinematic_state(q, qd) first")
+        block = state[0][i]                                       # [12, B]
+        return CoordinateTransform(rot=block[:9].t().reshape(-1, 3, 3), trans=block[9:12].t().contiguous(),
+                                   device=self._device)
+
+    def _body_vel(self, i):
+        from .spatial_vector_algebra import SpatialMotionVec
+        state = getattr(self, "_kin_state", None)
+        if state is None:
+            raise RuntimeError("no kinematic state: call update_kinematic_state(q, qd) first")
+        block = state[1][i]                                       # [6, B]: ang, lin
+        return SpatialMotionVec(lin_motion=block[3:6].t().contiguous(), ang_motion=block[0:3].t().contiguous())
+
+    @tensor_check
     def compute_forward_kinematics_all_links(self, q: torch.Tensor) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
-        r"""``{link_name: (pos, quat)}`` for every link (``robot_model.py:198-221``), one FK launch per link.
+        r"""``{link_name: (pos, quat)}`` for every link (``robot_model.py:198-221``) from ONE launch of the all-links
+        kernel (not differentiable; use ``compute_forward_kinematics`` per link when gradients are needed).
         Like the reference, 1-D inputs give un-squeezed ``[1, .]`` values (the dict bypasses the squeeze)."""
         self._check_q(q)
-        out = {}
-        for name in self.get_link_names():
-            pos, quat, _, _ = self._fk_jacobian(q, name, True, True, False)
-            out[name] = (pos, quat)
-        return out
+        with torch.no_grad():
+            poses, quats, _ = engine.kinematic_state_raw(self._topology, self._link_table().detach(), q, None,
+                                                         want_poses=True, want_quats=True)
+        return {name: (poses[i, 9:12].t().contiguous(), quats[i].t().contiguous())
+                for i, name in enumerate(self.get_link_names())}
 
     # ------------------------------------------------------------------------------------------
     # learnable link parameters (robot_model.py:669-713)

@@ -81,7 +81,9 @@ int drmb200_version(void);                 /* 10000*major + 100*minor + patch */
 const char* drmb200_last_error(void);      /* thread-local text of the last failure */
 int64_t drmb200_launch_count(void);        /* kernels launched by this library since load */
 /* Tuning knobs for A/B measurements (not part of the reference-facing surface):
- *   "fk_variant": 1 = TMA bulk-copy staging (default), 0 = cooperative float4 staging. */
+ *   "fk_variant": 1 = TMA bulk-copy staging (default), 0 = cooperative float4 staging;
+ *   "fk_tile":    configurations per CTA of the FK kernel, 64 / 128 / 256, 0 = chosen from the batch size (default);
+ *   "fk_unroll":  0 = rolled chain walk, 1 = unrolled register-Jacobian kernel (paths <= 8 links), 2 = auto (default). */
 int drmb200_set_option(const char* name, int value);
 
 /*
@@ -126,6 +128,17 @@ int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo,
                                       const float* g_tau,
                                       float* q_grad, float* qd_grad, float* qdd_grad,
                                       float* table_grad, void* workspace, void* cuda_stream);
+
+/*
+ * World pose (and body-frame spatial velocity) of EVERY link in one launch: replaces update_kinematic_state
+ * (robot_model.py:140-195) and, with `quats`, compute_forward_kinematics_all_links (robot_model.py:198-221).
+ * Outputs are link-major / component-major so that stores coalesce:
+ *   poses [n_links, 12, B]  rows 0..8 = R (row-major), 9..11 = p        (NULL to skip)
+ *   quats [n_links,  4, B]  xyzw                                        (NULL to skip)
+ *   vels  [n_links,  6, B]  ang(3), lin(3) in the link frame; needs qd  (NULL to skip)
+ */
+int drmb200_kinematic_state(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                            int64_t batch, float* poses, float* quats, float* vels, void* cuda_stream);
 
 /*
  * Link-parameter rows -> link table, and its adjoint (device pointers, asynchronous).

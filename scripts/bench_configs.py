@@ -93,8 +93,9 @@ def bench_train_step(batch):
     def step(_):
         for p in m.parameters():
             p.grad = None
-        pos, quat, jl, ja = m.compute_fk_and_jacobian(q, "iiwa_link_ee")
-        tau = m.compute_inverse_dynamics(q, qd, qdd)
+        with m.shared_link_table():
+            pos, quat, jl, ja = m.compute_fk_and_jacobian(q, "iiwa_link_ee")
+            tau = m.compute_inverse_dynamics(q, qd, qdd)
         loss = (tau - target).square().mean() + pos.square().mean()
         loss.backward()
 

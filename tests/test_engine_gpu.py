@@ -41,7 +41,7 @@ def fk_variant(request):
     engine.set_option("fk_tile", tile)
     yield request.param
     engine.set_option("fk_variant", 1)
-    engine.set_option("fk_unroll", 0)
+    engine.set_option("fk_unroll", 2)       # auto
     engine.set_option("fk_tile", 0)
 
 
