@@ -22,6 +22,7 @@ _lib = None
 
 GRAVITY = 1
 DAMPING = 2
+INERTIAL_GRADS_ONLY = 4      # backward hint: no kinematic link parameter is learnable (see include/drm_b200.h)
 
 _c_float_p = ctypes.c_void_p      # raw device / host addresses
 _SIGNATURES = {
@@ -263,9 +264,12 @@ class InverseDynamicsFunction(torch.autograd.Function):
         qd_grad = torch.empty_like(q) if need[2] else None
         qdd_grad = torch.empty_like(q) if need[3] else None
         ws = _workspace(ctx.topo, B, q.device)
+        flags = ctx.flags
+        if need[1] or need[2] or need[3] or not need[0]:
+            flags &= ~INERTIAL_GRADS_ONLY                   # the single-sweep kernel only produces table columns
         with torch.cuda.device(q.device):
             rc = lib().drmb200_inverse_dynamics_backward(
-                ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B, ctx.flags, _ptr(g_tau), _ptr(q_grad), _ptr(qd_grad), _ptr(qdd_grad),
+                ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B, flags, _ptr(g_tau), _ptr(q_grad), _ptr(qd_grad), _ptr(qdd_grad),
                 _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_inverse_dynamics_backward")
         return table_grad, q_grad, qd_grad, qdd_grad, None, None

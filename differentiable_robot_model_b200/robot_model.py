@@ -156,6 +156,21 @@ class DifferentiableRobotModel(torch.nn.Module):
             self._table_cache_key = key
         return self._table_cache
 
+    def _kinematic_params_learnable(self) -> bool:
+        """True if any joint origin (``trans`` / ``rot_angles`` of a movable link) is a learnable module with a
+        parameter that requires grad -- then the backward kernels must produce the F / r columns of the table
+        gradient; otherwise the RNEA backward can take the single-sweep inertial path."""
+        for body in self._bodies:
+            if body.joint_idx is None:
+                continue
+            for name in ("trans", "rot_angles"):
+                attr = getattr(body, name)
+                if isinstance(attr, torch.nn.Module):
+                    params = list(attr.parameters())
+                    if not params or any(p.requires_grad for p in params):      # parameter-free modules: be safe
+                        return True
+        return False
+
     def _check_q(self, *tensors):
         for t in tensors:
             assert t.ndim == 2
@@ -228,6 +243,8 @@ class DifferentiableRobotModel(torch.nn.Module):
         self._check_q(q, qd, qdd_des)
         flags = (engine.GRAVITY if include_gravity else 0) | (engine.DAMPING if use_damping else 0)
         table = self._link_table()
+        if not self._kinematic_params_learnable():
+            flags |= engine.INERTIAL_GRADS_ONLY     # backward hint: only (I_o, mc, m, damping) columns can matter
         if torch.is_grad_enabled() and (
             table.requires_grad or q.requires_grad or qd.requires_grad or qdd_des.requires_grad
         ):

@@ -62,6 +62,10 @@ extern "C" {
 /* flags for the dynamics entry points (robot_model.py:311-312) */
 #define DRMB200_GRAVITY 1u    /* include_gravity: base linear acceleration (0, 0, +9.81) */
 #define DRMB200_DAMPING 2u    /* use_damping: tau += damping * qd */
+/* drmb200_inverse_dynamics_backward only: the caller needs just the inertial columns of table_grad (I_o, mc, m)
+ * and the damping column -- nothing kinematic (F, r) is learnable and q_grad / qd_grad / qdd_grad are NULL.
+ * Selects a single-sweep kernel (~6x fewer instructions); the F / r columns of table_grad are left untouched. */
+#define DRMB200_INERTIAL_GRADS_ONLY 4u
 
 /*
  * Immutable kinematic-tree topology, host memory, links in URDF document order

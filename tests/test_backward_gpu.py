@@ -220,3 +220,43 @@ def test_learning_loop_reduces_loss():
         opt.step()
         losses.append(float(loss))
     assert losses[-1] < 0.2 * losses[0], losses[::10]
+
+
+@pytest.mark.parametrize("stem,batch,grav,damp", [("iiwa7", 70001, True, True), ("allegro_hand_description_left", 999, True, True),
+                                                  ("trifinger_edu", 130, False, False), ("iiwa7_allegro", 257, True, False)])
+def test_inertial_only_backward_matches_the_full_adjoint(stem, batch, grav, damp):
+    """With only mass / com / inertia_mat / damping learnable and no input gradients the RNEA backward takes the
+    single-sweep kernel (DRMB200_INERTIAL_GRADS_ONLY); its gradients must equal the full adjoint kernel's."""
+    from differentiable_robot_model_b200 import engine
+
+    def model(with_kinematic):
+        m = drm.DifferentiableRobotModel(urdf_path(stem), stem, device=DEV)
+        params = {}
+        for i, body in enumerate(m._bodies):
+            if i == 0:
+                continue
+            mods = {"mass": UnconstrainedScalar(init_val=body.inertia.mass().detach().clone()),
+                    "com": UnconstrainedTensor(1, 3, init_tensor=body.inertia.com().detach().clone().reshape(1, 3)),
+                    "inertia_mat": UnconstrainedTensor(3, 3, init_tensor=body.inertia.inertia_mat().detach().clone().reshape(3, 3))}
+            if body.joint_idx is not None:
+                mods["joint_damping"] = UnconstrainedScalar(init_val=body.joint_damping().detach().clone())
+                if with_kinematic:       # a learnable joint origin forces the full adjoint kernel
+                    mods["trans"] = UnconstrainedTensor(1, 3, init_tensor=body.trans().detach().clone().reshape(1, 3))
+            for pname, mod in mods.items():
+                m.make_link_param_learnable(body.name, pname, mod)
+                params[(i, pname)] = mod.param
+        return m, params
+
+    robot = O.load_robot(urdf_path(stem), torch.float32)
+    q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, batch, seed=11))
+    G = torch.randn(batch, robot.n_dofs, device=DEV)
+    grads = []
+    for with_kin in (False, True):
+        m, params = model(with_kin)
+        assert m._kinematic_params_learnable() == with_kin
+        tau = m.compute_inverse_dynamics(q, qd, qdd, include_gravity=grav, use_damping=damp)
+        (G * tau).sum().backward()
+        grads.append({k: p.grad.clone() for k, p in params.items() if k[1] != "trans"})
+    scale = max(float(g.abs().max()) for g in grads[1].values())
+    for k in grads[0]:
+        assert_close(grads[0][k].cpu().numpy(), grads[1][k].cpu().numpy(), rtol=1e-4, atol=1e-5 * max(scale, 1.0), what=str(k))
