@@ -167,12 +167,20 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # bounded sample per step so that steps + warmup finish within ~2 minutes
-    probe = time_cpu_port(4096, 0.0, 3)
-    per_cfg = sorted(probe)[len(probe) // 2] / 4096
-    budget = 100.0 / max(1, args.steps + args.warmup)
-    batch = int(max(256, min(BATCH, budget / per_cfg)))
-    times = time_cpu_port(batch, 0.0, args.steps, warmup=max(1, min(args.warmup, 3)))
+    # Bounded sample per step so that steps + warmup finish within ~2 minutes.  One call of the port costs
+    # t0 + c * batch (t0 = the dispatch overhead of its ~2 k small torch ops): fit both from two probes.
+    if args.steps is None:
+        args.steps = 20                                   # CPU arm default; the GPU arm's default would take hours
+    lo = sorted(time_cpu_port(256, 0.0, 3))[1]
+    hi = sorted(time_cpu_port(4096, 0.0, 3))[1]
+    c = max((hi - lo) / (4096 - 256), 1e-9)
+    t0 = max(lo - 256 * c, 0.0)
+    per_step = 100.0 / max(1, args.steps + min(args.warmup, 3))
+    batch = int(max(256, min(BATCH, (per_step - t0) / c)))
+    max_steps = args.steps
+    if t0 + 256 * c > per_step:                           # K steps do not fit even at the smallest sample:
+        max_steps = max(3, int(100.0 / (t0 + 256 * c)))   # time as many as fit and say so
+    times = time_cpu_port(batch, float("inf"), max_steps, warmup=max(1, min(args.warmup, 3)))   # exactly max_steps calls
     total = sum(times)
     value = batch * len(times) / total
     cores = _CPU_THREADS
@@ -181,7 +189,8 @@ def run_reference_arm(args):
               f"{cores} intra-op threads (fastest of the probed counts on this {os.cpu_count()}-core host)")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "steps": len(times), "requested_steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "Kuka iiwa 7-DoF FK + end-effector Jacobian (BASELINE.json configs[1])",
                    "batch_per_step": batch, "ee_link": EE_LINK},
@@ -197,7 +206,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200000)
+    ap.add_argument("--steps", type=int, default=None, help="default 200000 (GPU arm) / 20 (--impl reference)")
     ap.add_argument("--warmup", type=int, default=2000)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -209,6 +218,9 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.steps is None:
+        args.steps = 200000
+    args.steps = max(args.steps, 1)
 
     import torch.distributed as dist
     import differentiable_robot_model_b200 as drm
@@ -249,32 +261,39 @@ def main():
             step(i)
         stream.synchronize()
         nodes = max(1, min(GRAPH_NODES, args.steps))
-        nodes -= nodes % ROTATE if nodes >= ROTATE else 0
         # Steps are independent batches, so the graph forks into INFLIGHT parallel branches: a
         # 65 536-configuration launch fills only half a wave of the GPU, and several in flight hide each
         # other's ramp-up / drain (set DRMB200_BENCH_INFLIGHT=1 for strictly serialised launches).
         inflight = max(1, min(int(os.environ.get("DRMB200_BENCH_INFLIGHT", "4")), ROTATE, nodes))
         side = [torch.cuda.Stream(device=dev) for _ in range(inflight - 1)]
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=stream):
-            fork = torch.cuda.Event()
-            fork.record(stream)
-            for s in side:
-                s.wait_event(fork)
-            for i in range(nodes):
-                lane = i % inflight
-                if lane == 0:
-                    step(i)
-                else:
-                    with torch.cuda.stream(side[lane - 1]):
+
+        def capture(n_nodes, first):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                fork = torch.cuda.Event()
+                fork.record(stream)
+                for s in side:
+                    s.wait_event(fork)
+                for i in range(first, first + n_nodes):
+                    lane = i % inflight
+                    if lane == 0:
                         step(i)
-            for s in side:
-                join = torch.cuda.Event()
-                join.record(s)
-                stream.wait_event(join)
+                    else:
+                        with torch.cuda.stream(side[lane - 1]):
+                            step(i)
+                for s in side:
+                    join = torch.cuda.Event()
+                    join.record(s)
+                    stream.wait_event(join)
+            return g
+
+        graph = capture(nodes, 0)
         replays, rest = divmod(args.steps, nodes)
+        tail_graph = capture(rest, replays * nodes) if rest else None      # the remainder is graph-launched too
         for _ in range(max(1, (args.warmup - 64) // nodes)):
             graph.replay()
+        if tail_graph is not None:
+            tail_graph.replay()
         stream.synchronize()
 
         def barrier():
@@ -291,8 +310,8 @@ def main():
         ev0.record(stream)
         for _ in range(replays):
             graph.replay()
-        for i in range(rest):
-            step(i)
+        if tail_graph is not None:
+            tail_graph.replay()
         ev1.record(stream)
         stream.synchronize()
         if sampler:
@@ -303,8 +322,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms = float(t.item())
-    gpu_launches = replays * nodes + rest
-    assert engine.launch_count() - launches_before == rest       # graph replays bypass the library counter
+    gpu_launches = replays * nodes + rest                        # one fk_jacobian_kernel launch per step
+    assert engine.launch_count() - launches_before == 0          # all replayed from graphs: no host-side launches
 
     value = world * args.steps * BATCH / (elapsed_ms * 1e-3)
     peak, peak_src = measured_peak_gbs()
@@ -321,7 +340,7 @@ def main():
                    "parallelism": f"batch-sharded x{world}, no data-path collective",
                    "l2_policy": f"rotating {ROTATE} distinct buffer sets ({ROTATE * BATCH * BYTES_PER_CONFIG / 1e6:.0f} MB) > L2",
                    "launch": f"CUDA graph of {nodes} kernel nodes in {inflight} parallel branches (independent "
-                             f"batches in flight) replayed {replays}x + {rest} direct launches"},
+                             f"batches in flight) replayed {replays}x + one {rest}-node tail graph"},
         "gpu_launches": gpu_launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "peak_source": peak_src, "kernel": "fk_jacobian_kernel<WITH_JAC, TMA bulk>",

@@ -262,11 +262,17 @@ fk_jacobian_backward_kernel(const __grid_constant__ PathProgram prog, const FkBw
 // sums the per-CTA partial tables in fixed order and ADDS them to table_grad
 __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n_blocks, int n_entries,
                                        float* __restrict__ table_grad) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per table entry: lanes stride over the CTA partials (fixed assignment -> fixed summation order),
+    // then a shuffle tree.  (One thread per entry looping over ~1200 partials took 35 us, longer than the
+    // single-sweep backward kernel it follows.)
+    const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (e >= n_entries) return;
     float s = 0.f;
-    for (int b = 0; b < n_blocks; ++b) s += partials[(size_t)b * n_entries + e];
-    table_grad[e] += s;
+    for (int b = lane; b < n_blocks; b += 32) s += partials[(size_t)b * n_entries + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) table_grad[e] += s;
 }
 
 int64_t table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch) {
@@ -296,7 +302,7 @@ static int persistent_grid(Kern kern, int block, size_t smem_bytes, int64_t tile
 static int launch_reduce(const float* partials, int grid, const drmb200_topology_t* topo, float* table_grad,
                          cudaStream_t stream) {
     const int entries = topo->n_links * DRMB200_TABLE_STRIDE;
-    reduce_partials_kernel<<<(entries + 127) / 128, 128, 0, stream>>>(partials, grid, entries, table_grad);
+    reduce_partials_kernel<<<(entries * 32 + 255) / 256, 256, 0, stream>>>(partials, grid, entries, table_grad);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("reduce launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();

@@ -31,7 +31,7 @@
 
 namespace drm {
 
-constexpr int RNEA_TILE = 128;
+// configurations per CTA: template parameter T of the kernel, 64 or 128 (see inverse_dynamics_device)
 constexpr float GRAVITY = 9.81f;     // robot_model.py:347
 
 struct RneaArgs {
@@ -47,7 +47,7 @@ struct RneaArgs {
 
 struct RneaSmemLayout {
     int q, qd, qdd, tau, table, link, slots, total_floats;
-    __host__ __device__ RneaSmemLayout(int n, int n_links, int n_slots) {
+    __host__ __device__ RneaSmemLayout(int RNEA_TILE, int n, int n_links, int n_slots) {
         int o = 0;
         q = o;   o += RNEA_TILE * n;
         qd = o;  o += RNEA_TILE * n;
@@ -72,14 +72,15 @@ __device__ __forceinline__ void stage_canonical_table(float* s_tab, const float*
     }
 }
 
-__global__ void __launch_bounds__(RNEA_TILE, 4)
+template <int T>
+__global__ void __launch_bounds__(T)
 rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t mbar;
 
     const int n = prog.n_dofs;
     const int N = prog.n_links;
-    const RneaSmemLayout L(n, N, prog.n_slots);
+    const RneaSmemLayout L(T, n, N, prog.n_slots);
     float* s_q = smem + L.q;
     float* s_qd = smem + L.qd;
     float* s_qdd = smem + L.qdd;
@@ -87,7 +88,6 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
     float* s_tab = smem + L.table;
     float* s_link = smem + L.link;
     float* s_slot = smem + L.slots;
-    constexpr int T = RNEA_TILE;
 
     const int tid = threadIdx.x;
     const int64_t tile_start = (int64_t)blockIdx.x * T;
@@ -273,7 +273,11 @@ int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
     if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr || qd == nullptr || qdd == nullptr || tau == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
-    const int64_t tiles = (batch + RNEA_TILE - 1) / RNEA_TILE;
+    // tile: 64 for batches that would not fill two waves of 128-row CTAs (more, smaller CTAs balance the SMs and the
+    // shared-memory-limited residency is the same number of warps), and for models whose 128-row footprint is too big
+    int tile = (batch <= 148 * 1024) ? 64 : 128;
+    if ((size_t)RneaSmemLayout(128, prog.n_dofs, prog.n_links, prog.n_slots).total_floats * sizeof(float) > 110 * 1024) tile = 64;
+    const int64_t tiles = (batch + tile - 1) / tile;
     if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
 
     RneaArgs args;
@@ -281,19 +285,22 @@ int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
 
-    const RneaSmemLayout L(prog.n_dofs, prog.n_links, prog.n_slots);
+    const RneaSmemLayout L(tile, prog.n_dofs, prog.n_links, prog.n_slots);
     const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
-    static size_t configured_by_dev[64] = {0};
+    static size_t configured_by_dev[2][64] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
-    size_t& configured = configured_by_dev[dev & 63];
+    size_t& configured = configured_by_dev[tile == 64 ? 0 : 1][dev & 63];
     if (smem_bytes > configured) {
-        cudaError_t e = cudaFuncSetAttribute(rnea_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaError_t e = tile == 64
+            ? cudaFuncSetAttribute(rnea_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
+            : cudaFuncSetAttribute(rnea_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
         configured = smem_bytes;
     }
-    rnea_kernel<<<(unsigned)tiles, RNEA_TILE, smem_bytes, stream>>>(prog, args);
+    if (tile == 64) rnea_kernel<64><<<(unsigned)tiles, 64, smem_bytes, stream>>>(prog, args);
+    else rnea_kernel<128><<<(unsigned)tiles, 128, smem_bytes, stream>>>(prog, args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("rnea launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();

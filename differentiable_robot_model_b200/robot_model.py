@@ -15,8 +15,9 @@ on the caller's current CUDA stream, with analytic backward kernels registered t
 
 Deliberate deviations from the reference:
   * compute entry points need a CUDA model and CUDA fp32 tensors -- there is no CPU path;
-  * per-body mutable state (``_bodies[i].pose / vel / acc / force``) is not materialised by the
-    fused kernels (nothing is written per link to HBM);
+  * per-body state ``_bodies[i].pose / vel`` is refreshed only by ``update_kinematic_state`` (one
+    all-links launch), not as a side effect of every call; ``acc / force`` are not materialised
+    (the fused kernels write nothing per link to HBM);
   * ``recursive=True`` FK returns the same (correct) result as the non-recursive path; the
     reference's recursive variant depends on stale per-body state (``rigid_body.py:119``);
   * joint axes must be signed coordinate axes (true for every shipped URDF).

@@ -29,17 +29,50 @@ except Exception:
     pass
 
 
-def timed(fn, iters, warmup=5):
+def timed(fn, iters, warmup=5, inflight=4, n_sets=8):
+    """ms per call.  Small launches (iters >= 100) are replayed from a CUDA graph with `inflight` independent
+    calls in flight on parallel branches (like bench.py); big ones are launched back to back."""
     for i in range(warmup):
         fn(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        fn(i)
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters          # ms per call
+    if iters < 100:
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+    stream = torch.cuda.Stream()
+    inflight = min(inflight, n_sets)
+    side = [torch.cuda.Stream() for _ in range(inflight - 1)]
+    nodes = 128
+    with torch.cuda.stream(stream):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            for s in side:
+                s.wait_event(fork)
+            for i in range(nodes):
+                if i % inflight == 0:
+                    fn(i)
+                else:
+                    with torch.cuda.stream(side[i % inflight - 1]):
+                        fn(i)
+            for s in side:
+                j = torch.cuda.Event()
+                j.record(s)
+                stream.wait_event(j)
+        g.replay()
+        stream.synchronize()
+        reps = max(1, iters // nodes) * 8
+        e0.record(stream)
+        for _ in range(reps):
+            g.replay()
+        e1.record(stream)
+        stream.synchronize()
+    return e0.elapsed_time(e1) / (reps * nodes)
 
 
 def rotate_count(bytes_per_set):
