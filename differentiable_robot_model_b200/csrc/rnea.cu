@@ -262,6 +262,10 @@ int build_tree_program(const drmb200_topology_t* topo, TreeProgram* prog) {
         }
     }
     prog->n_slots = n_slots;
+    int n_tips = 0;
+    prog->tip[0] = -1;
+    for (int i = 1; i < N; ++i) prog->tip[i] = (i + 1 < N && topo->parent[i + 1] == i) ? (int8_t)-1 : (int8_t)n_tips++;
+    prog->n_tips = n_tips;
     return DRMB200_OK;
 }
 

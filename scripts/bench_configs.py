@@ -110,6 +110,42 @@ def bench_fk(model, link, batch):
             "hbm_frac": batch * by / ms / 1e6 / PEAK}
 
 
+def bench_backward_kernels(batch):
+    """Raw launches of the analytic adjoint kernels (Kuka): FK/Jacobian backward, full RNEA backward, inertial-only."""
+    import ctypes
+    m = drm.DifferentiableKUKAiiwa(device=DEV)
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, batch, seed=0))
+    table, topo, ee = m._link_table(), m._topology, m._name_to_idx_map["iiwa_link_ee"]
+    g_pos, g_quat = torch.randn(batch, 3, device=DEV), torch.randn(batch, 4, device=DEV)
+    g_jl, g_ja = torch.randn(batch, 3, 7, device=DEV), torch.randn(batch, 3, 7, device=DEV)
+    g_tau = torch.randn(batch, 7, device=DEV)
+    qg, tg = torch.empty_like(q), torch.zeros_like(table)
+    ws = engine._workspace(topo, batch, DEV)
+    lib, P, S = engine.lib(), engine._ptr, engine._stream
+    out = {"batch": batch}
+
+    def fk_bwd(with_table):
+        rc = lib.drmb200_fk_jacobian_backward(ctypes.byref(topo), ee, P(table), P(q), batch, P(g_pos), P(g_quat), P(g_jl),
+                                              P(g_ja), P(qg), P(tg) if with_table else None, P(ws), S())
+        assert rc == 0
+
+    def id_bwd(flags, inputs):
+        rc = lib.drmb200_inverse_dynamics_backward(ctypes.byref(topo), P(table), P(q), P(qd), P(qdd), batch, flags, P(g_tau),
+                                                   P(qg) if inputs else None, P(qg) if inputs else None,
+                                                   P(qg) if inputs else None, P(tg), P(ws), S())
+        assert rc == 0
+
+    for name, fn, by in (("fk_jacobian_backward_q_only", lambda i: fk_bwd(False), 28 + 28 + 168 + 28),
+                         ("fk_jacobian_backward_q_and_table", lambda i: fk_bwd(True), 28 + 28 + 168 + 28),
+                         ("rnea_backward_full", lambda i: id_bwd(3, True), 28 * 7),
+                         ("rnea_backward_inertial_only", lambda i: id_bwd(3 | 4, False), 16 * 7)):
+        ms = timed(fn, 20)
+        out[name] = {"ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
+                     "achieved_GBps": batch * by / ms / 1e6}
+    return out
+
+
 def bench_train_step(batch):
     """config 5 on one shard: FK+Jacobian + RNEA forward, scalar loss, backward to 21 inertial tensors."""
     m = drm.DifferentiableKUKAiiwa(device=DEV)
@@ -148,6 +184,7 @@ def main():
                                                              "allegro/urdf/allegro_hand_description_left.urdf")
     out["config4_allegro_fk_jac"] = [bench_fk(allegro, "link_15.0_tip", b) for b in (32768, 1 << 21)]
     out["config5_kuka_train_step"] = [bench_train_step(b) for b in (131072,)]
+    out["kuka_backward_kernels"] = [bench_backward_kernels(131072)]
     print(json.dumps(out))
 
 
