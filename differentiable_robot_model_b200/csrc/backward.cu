@@ -51,7 +51,7 @@ struct FkBwdSmem {
         gjl = o; o += tile * 3 * n;
         gja = o; o += tile * 3 * n;
         table = o; o += len * 12;
-        link = o; o += len * 14 * tile;                  // per path link: R~ (9), p (3), cos, sin -- slot-major
+        link = o; o += len * 2 * tile;                   // per path link: cos, sin -- slot-major (R~, p are re-derived)
         scratch = o; o += 12 * (tile + 1);
         acc = o; o += len * 12;                          // canonical (F~, r~) gradient per path link
         total_floats = o;
@@ -121,26 +121,29 @@ fk_jacobian_backward_kernel(const __grid_constant__ PathProgram prog, const FkBw
                 pbar = cross_add(g, col2(R), pbar);         // adjoint of p_ee: J_lin = z x (p_ee - p_i)
                 rotate_z(R, cs, sn);
             }
-            float* s = lk + k * 14 * T;
-            stm(s, T, R);
-            stv(s + 9 * T, T, p);
-            s[12 * T] = cs; s[13 * T] = sn;
+            float* s = lk + k * 2 * T;
+            s[0] = cs; s[T] = sn;
         }
         const V3 p_ee = p;
         const float4 gq = reinterpret_cast<const float4*>(s_gquat)[tid];
         M3 Rbar = permute_cols_adjoint(quat_backward(unpermute_cols(R, prog.ee_axis), gq), prog.ee_axis);
 
         // ---- reverse sweep ee -> root ------------------------------------------------------------
+        // The chain is walked back DOWN in registers: R~_{k-1} = R~_k M_k^T and p_{k-1} = p_k - R~_{k-1} r_k (M_k is
+        // orthogonal), so only (cos, sin) per link live in shared memory -- 2 floats instead of 14 per link, which
+        // is what bounds the occupancy of this kernel.  The re-derived poses differ from the forward ones by rounding.
         M3 Rk = R;                                          // R~_k of the link being processed
+        V3 pk = p;
         for (int k = len - 1; k >= 0; --k) {
-            const float* s = lk + k * 14 * T;
-            const V3 pk = ldv(s + 9 * T, T);
-            const float cs = s[12 * T], sn = s[13 * T];
-            const M3 RP = (k > 0) ? ldm(lk + (k - 1) * 14 * T, T) : identity3();
+            const float* s = lk + k * 2 * T;
+            const float cs = s[0], sn = s[T];
             M3 F; V3 r;
             load_Fr(s_tab + k * 12, F, r);
             const int c = prog.dof[k];
             M3 M = F;
+            if (c >= 0) rotate_z(M, cs, sn);
+            const M3 RP = (k > 0) ? mulNT(Rk, M) : identity3();
+            const V3 pP = (k > 0) ? pk - mul(RP, r) : v3(0.f, 0.f, 0.f);
             if (c >= 0) {
                 const V3 z = col2(Rk);
                 const V3 g = v3(gl[c], gl[n + c], gl[2 * n + c]);
@@ -148,7 +151,6 @@ fk_jacobian_backward_kernel(const __grid_constant__ PathProgram prog, const FkBw
                 const V3 zbar = cross_add(p_ee - pk, g, h);   // d x G_l + G_a
                 Rbar.a02 += zbar.x; Rbar.a12 += zbar.y; Rbar.a22 += zbar.z;    // z = R~_k e_z
                 pbar = pbar - cross(g, z);                    // adjoint of p_k
-                rotate_z(M, cs, sn);
             }
             const M3 Mbar = mulTN(RP, Rbar);
             const V3 rbar = mulT(RP, pbar);
@@ -165,6 +167,7 @@ fk_jacobian_backward_kernel(const __grid_constant__ PathProgram prog, const FkBw
             }
             Rbar = Rbar_P;
             Rk = RP;
+            pk = pP;
         }
         if (args.q_grad != nullptr) {
             __syncthreads();
