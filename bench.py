@@ -420,6 +420,24 @@ def main():
                           f"{cores} intra-op threads (fastest probed on this {os.cpu_count()}-core host), "
                           f"{sum(times):.1f} s",
             }
+            # context: the reference AS SHIPPED evaluates the quaternion in a Python loop over batch elements
+            # (spatial_vector_algebra.py:116-135); time the port with that loop on a small sample
+            try:
+                from oracle import drm_oracle as O3
+                rb3 = O3.load_robot(model.urdf_path, torch.float32)
+                q3, _, _ = O3.sample_inputs(rb3, 2048, seed=0)
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    R3, p3, _, _, _ = O3.kinematic_state(rb3, q3)
+                    O3.quaternion_per_element(R3[rb3.index(EE_LINK)])
+                    O3.jacobian(rb3, q3, EE_LINK)
+                result["cpu_baseline_as_shipped"] = {
+                    "value": 2048 / (time.perf_counter() - t0), "unit": UNIT, "cores": _CPU_THREADS, "kind": "port",
+                    "sample": "2048 configurations with the reference's per-element Python quaternion loop restated "
+                              "(oracle.drm_oracle.quaternion_per_element); the survey measured 8.6 k cfg/s for the real "
+                              "reference at batch 65 536 on an 8-vCPU host"}
+            except Exception as exc:
+                result["cpu_baseline_as_shipped"] = {"error": str(exc)}
             # context: the scalar C restatement of the same algorithm on all cores (oracle/drm_oracle.c)
             try:
                 from oracle.c_oracle import CRobot

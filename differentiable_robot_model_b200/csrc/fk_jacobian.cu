@@ -164,6 +164,38 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
             const uint32_t a_q = smem_addr_opaque(qrow);
             const uint32_t a_jl = smem_addr_opaque(jl), a_ja = smem_addr_opaque(ja);
             const uint32_t n4 = 4u * n;
+            if (MAXLEN < 0) {
+                // packed FP32x2 walk (FFMA2 / FMUL2): rows 0,1 of R and (p.x, p.y) live in 64-bit register pairs;
+                // 35 instead of 54 arithmetic instructions per movable link, same operations in the same order
+                M3P Rp = identity3p();
+                f32x2 pp = pk2(0.f, 0.f);
+                float p2 = 0.f;
+                for (int k = 0; k < len; ++k, a_tab += 48) {
+                    M3 F; V3 r;
+                    load_Fr_s(a_tab, F, r);
+                    mul_add_p(Rp, r, pp, p2);
+                    Rp = mul_p(Rp, F);
+                    const int c = prog.dof[k];
+                    if (c >= 0) {
+                        float sn, cs;
+                        sincos_pi2(lds_f32(a_q + 4u * c), sn, cs);
+                        if (WITH_JAC) {
+                            float zx, zy, px, py;
+                            upk2(Rp.c2, zx, zy);
+                            upk2(pp, px, py);
+                            const V3 z = v3(zx, zy, Rp.a22);
+                            const V3 m = cross(z, v3(px, py, p2));
+                            const uint32_t o = 4u * c;
+                            sts_f32(a_ja + o, z.x); sts_f32(a_ja + o + n4, z.y); sts_f32(a_ja + o + 2 * n4, z.z);
+                            sts_f32(a_jl + o, m.x); sts_f32(a_jl + o + n4, m.y); sts_f32(a_jl + o + 2 * n4, m.z);
+                        }
+                        rotate_z_p(Rp, cs, sn);
+                    }
+                }
+                R = unpack3(Rp);
+                upk2(pp, p.x, p.y);
+                p.z = p2;
+            } else {
             for (int k = 0; k < len; ++k, a_tab += 48) {
                 M3 F; V3 r;
                 load_Fr_s(a_tab, F, r);
@@ -182,6 +214,7 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
                     }
                     rotate_z(R, cs, sn);
                 }
+            }
             }
             if (WITH_JAC) {
                 // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
@@ -312,8 +345,10 @@ static int launch_fk_l(const PathProgram& prog, const FkArgs& args, cudaStream_t
     // kernel touches the J tile once per column instead of three times and wins (Allegro, n = 16: 9.8 vs 6.3 G cfg/s).
     const int opt = get_option(2);                     // 0 rolled, 1 unrolled, 2 auto
     const bool unrolled = prog.len <= 8 && (opt == 1 || (opt != 0 && (prog.n_dofs % 2) == 0));
-    return unrolled ? launch_fk<NDOF, TILE, WITH_JAC, 8>(prog, args, stream)
-                    : launch_fk<NDOF, TILE, WITH_JAC, 0>(prog, args, stream);
+    if (unrolled) return launch_fk<NDOF, TILE, WITH_JAC, 8>(prog, args, stream);
+    // rolled walk: packed FP32x2 arithmetic (FFMA2) unless switched off for A/B measurements
+    return get_option(3) != 0 ? launch_fk<NDOF, TILE, WITH_JAC, -1>(prog, args, stream)
+                              : launch_fk<NDOF, TILE, WITH_JAC, 0>(prog, args, stream);
 }
 template <int NDOF, int TILE>
 static int launch_fk_j(bool with_jac, const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {

@@ -32,11 +32,14 @@ def main():
                torch.empty(big, 3, 7, device=DEV))
     stream = torch.cuda.Stream(device=DEV)
     rows = []
-    for variant, unroll, tile in itertools.product((1, 0), (1, 0), (64, 128, 256)):
+    combos = [(1, 0, 1), (1, 0, 0), (1, 1, 0), (0, 0, 1)]      # (staging, unrolled, packed FP32x2)
+    for (variant, unroll, packed), tile in itertools.product(combos, (64, 128, 256)):
         engine.set_option("fk_variant", variant)
         engine.set_option("fk_unroll", unroll)
+        engine.set_option("fk_packed", packed)
         engine.set_option("fk_tile", tile)
-        row = {"staging": "tma_bulk" if variant else "coop", "unrolled": bool(unroll), "tile": tile}
+        row = {"staging": "tma_bulk" if variant else "coop", "unrolled": bool(unroll), "packed_f32x2": bool(packed),
+               "tile": tile}
         with torch.cuda.stream(stream):
             # large batch
             for _ in range(3):
@@ -87,7 +90,7 @@ def main():
                 row[f"small_us_per_launch_inflight{inflight}"] = us
                 row[f"small_Gcfg_s_inflight{inflight}"] = small / us / 1e3
         rows.append(row)
-    engine.set_option("fk_variant", 1); engine.set_option("fk_unroll", 1); engine.set_option("fk_tile", 0)
+    engine.set_option("fk_variant", 1); engine.set_option("fk_unroll", 2); engine.set_option("fk_packed", 1); engine.set_option("fk_tile", 0)
     print(json.dumps({"gpu": torch.cuda.get_device_name(0), "rows": rows}))
 
 

@@ -44,3 +44,20 @@ def test_c_oracle_matches_torch_oracle_and_is_thread_count_independent():
     assert_close(outs1[3], ja.numpy(), rtol=1e-10, atol=1e-12, what="jang")
     tau = c.inverse_dynamics(q.numpy(), qd.numpy(), qdd.numpy())
     assert_close(tau, O.inverse_dynamics(robot, q, qd, qdd).numpy(), rtol=1e-9, atol=1e-10, what="tau")
+
+
+def test_per_element_quaternion_loop_matches_vectorised_and_reference_golden():
+    """oracle.quaternion_per_element restates the reference's shipped Python loop; it must agree with the vectorised
+    oracle (same branches, same signs) and with the reference's own outputs."""
+    g = load_golden("iiwa7_allegro")
+    robot = O.load_robot(urdf_path("iiwa7_allegro"), torch.float32)
+    q = torch.tensor(g["q"])
+    R, _, _, _, _ = O.kinematic_state(robot, q)
+    for link in g["fk_links"].tolist():
+        Ri = R[robot.index(link)]
+        loop, vec = O.quaternion_per_element(Ri), O.quaternion(Ri)
+        assert_close(loop.numpy(), vec.numpy(), rtol=1e-6, atol=1e-7, what="loop vs vectorised")
+        assert_close(canon_quat(loop.numpy()), canon_quat(g[f"quat.{link}"]), what="loop vs reference")
+    Rrand = torch.linalg.qr(torch.randn(257, 3, 3, generator=torch.Generator().manual_seed(0)))[0]
+    Rrand = Rrand * torch.sign(torch.linalg.det(Rrand))[:, None, None]            # proper rotations, all four branches
+    assert_close(O.quaternion_per_element(Rrand).numpy(), O.quaternion(Rrand).numpy(), rtol=1e-5, atol=1e-6, what="random R")

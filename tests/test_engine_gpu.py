@@ -31,18 +31,20 @@ def cuda(a):
     return torch.tensor(np.asarray(a), dtype=torch.float32, device=DEV)
 
 
-@pytest.fixture(params=[(1, 0, 0), (0, 0, 0), (1, 1, 64), (1, 0, 256)],
-                ids=["tma_bulk", "coop_copy", "unrolled_tile64", "tile256"])
+@pytest.fixture(params=[(1, 0, 0, 1), (0, 0, 0, 1), (1, 1, 64, 1), (1, 0, 256, 0)],
+                ids=["tma_bulk_packed", "coop_copy_packed", "unrolled_tile64", "tile256_scalar"])
 def fk_variant(request):
-    """Every staging / unrolling / tile variant of the FK kernel must give the same parity."""
-    variant, unroll, tile = request.param
+    """Every staging / unrolling / tile / packed-arithmetic variant of the FK kernel must give the same parity."""
+    variant, unroll, tile, packed = request.param
     engine.set_option("fk_variant", variant)
     engine.set_option("fk_unroll", unroll)
     engine.set_option("fk_tile", tile)
+    engine.set_option("fk_packed", packed)
     yield request.param
     engine.set_option("fk_variant", 1)
     engine.set_option("fk_unroll", 2)       # auto
     engine.set_option("fk_tile", 0)
+    engine.set_option("fk_packed", 1)
 
 
 # ------------------------------------------------------------------------------------------------
