@@ -60,16 +60,29 @@ struct FkSmemLayout {
 // One link of the chain walk: p <- R r + p ; R <- R F~ ; for movable joints record the joint axis
 // z (third column, unchanged by the z rotation) and m = z x p_i, then R <- R Rz(q).
 template <bool FIRST, bool WITH_JAC>
-__device__ __forceinline__ void walk_link(const float* row, const float* qrow, int c, M3& R, V3& p, V3& z, V3& m) {
+__device__ __forceinline__ void walk_link(const float* row, const float* qrow, int c, M3P& R, f32x2& pp, float& p2,
+                                          V3& z, V3& m) {
     M3 F; V3 r;
     load_Fr(row, F, r);
-    if (FIRST) { p = r; R = F; }             // parent is the root: R = I, p = 0
-    else { p = mul_add(R, r, p); R = mul(R, F); }
+    if (FIRST) {                             // parent is the root: R = I, p = 0
+        pp = pk2(r.x, r.y); p2 = r.z;
+        R.c0 = pk2(F.a00, F.a10); R.c1 = pk2(F.a01, F.a11); R.c2 = pk2(F.a02, F.a12);
+        R.a20 = F.a20; R.a21 = F.a21; R.a22 = F.a22;
+    } else {
+        mul_add_p(R, r, pp, p2);
+        R = mul_p(R, F);
+    }
     if (c >= 0) {
         float sn, cs;
         sincos_pi2(qrow[c], sn, cs);
-        if (WITH_JAC) { z = col2(R); m = cross(z, p); }
-        rotate_z(R, cs, sn);
+        if (WITH_JAC) {
+            float zx, zy, px, py;
+            upk2(R.c2, zx, zy);
+            upk2(pp, px, py);
+            z = v3(zx, zy, R.a22);
+            m = cross(z, v3(px, py, p2));
+        }
+        rotate_z_p(R, cs, sn);
     }
 }
 
@@ -135,14 +148,20 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
 
         if (MAXLEN > 0) {
             V3 zs[MAXLEN > 0 ? MAXLEN : 1], ms[MAXLEN > 0 ? MAXLEN : 1];
+            M3P Rp = identity3p();           // packed FP32x2 state (FFMA2 arithmetic), see drm_common.cuh
+            f32x2 pp = pk2(0.f, 0.f);
+            float p2 = 0.f;
 #pragma unroll
             for (int k = 0; k < MAXLEN; ++k) {
                 zs[k] = ms[k] = v3(0.f, 0.f, 0.f);
                 if (k < len) {
-                    if (k == 0) walk_link<true, WITH_JAC>(s_tab, qrow, prog.dof[0], R, p, zs[0], ms[0]);
-                    else walk_link<false, WITH_JAC>(s_tab + k * 12, qrow, prog.dof[k], R, p, zs[k], ms[k]);
+                    if (k == 0) walk_link<true, WITH_JAC>(s_tab, qrow, prog.dof[0], Rp, pp, p2, zs[0], ms[0]);
+                    else walk_link<false, WITH_JAC>(s_tab + k * 12, qrow, prog.dof[k], Rp, pp, p2, zs[k], ms[k]);
                 }
             }
+            R = unpack3(Rp);
+            upk2(pp, p.x, p.y);
+            p.z = p2;
             if (WITH_JAC) {
                 // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
 #pragma unroll
