@@ -317,6 +317,82 @@ def inverse_dynamics(robot, q, qd, qdd, include_gravity=True, use_damping=True):
     return tau
 
 
+def _spatial_inertia(robot, i):
+    """get_spatial_mat (spatial_vector_algebra.py:340-372): 6x6 in [ang; lin] order, NOT symmetrised."""
+    m, c, Ic = robot.mass[i], robot.com[i], robot.inertia[i]
+    S = _skew(c.unsqueeze(0))[0]
+    Io = Ic + m * (S @ S.t())
+    Smc = _skew((m * c).unsqueeze(0))[0]
+    top = torch.cat([Io, Smc], dim=1)
+    bot = torch.cat([Smc.t(), m * torch.eye(3, dtype=Ic.dtype)], dim=1)
+    return torch.cat([top, bot], dim=0)
+
+
+def _motion_matrix(Rj, tj):
+    """CoordinateTransform.to_matrix (spatial_vector_algebra.py:138-154): [[R^T, 0], [-R^T t^, R^T]]."""
+    B = Rj.shape[0]
+    Rt = Rj.transpose(-2, -1)
+    top = torch.cat([Rt, torch.zeros(B, 3, 3, dtype=Rj.dtype)], dim=2)
+    bot = torch.cat([-(Rt @ _skew(tj.expand(B, 3))), Rt], dim=2)
+    return torch.cat([top, bot], dim=1)
+
+
+def forward_dynamics(robot, q, qd, f, include_gravity=True, use_damping=False):
+    """Articulated-body algorithm exactly as the reference evaluates it (robot_model.py:488-624), including its
+    use of the COLUMN U = IA S in both the rank-1 update and the joint-acceleration formula (so for a
+    non-symmetric inertia_mat the result is the reference's, not H^-1 (f - nle)), the +1e-37 regularisers
+    (:570, :582) and zero-axis "joints" for fixed links.  The reference additionally overwrites the caller's f
+    in place when use_damping is set (:521); this restatement leaves f untouched.
+    Spatial vectors are [ang; lin] (get_vector, sva:238-239)."""
+    B = q.shape[0]
+    N = len(robot.names)
+    dt = q.dtype
+    if use_damping:
+        f = f - torch.stack([robot.damping[i] for i in robot.controlled]).unsqueeze(0) * qd
+    R, p, w, v, joints = kinematic_state(robot, q, qd)
+    zeros = torch.zeros(B, 3, dtype=dt)
+    g = torch.stack([zeros[:, 0], zeros[:, 0], (9.81 if include_gravity else 0.0) * torch.ones(B, dtype=dt)], dim=1)
+    c, pA, IA = [None] * N, [None] * N, [None] * N
+    for i in range(1, N):
+        jw = qd[:, robot.dof[i]:robot.dof[i] + 1] @ robot.axis[i:i + 1] if robot.dof[i] >= 0 else zeros
+        c[i] = torch.cat([_cross(w[i], jw), _cross(v[i], jw)], dim=1)            # cross_motion_vec, joint_vel.lin = 0
+        h_lin, h_ang = _inertia_times(robot, i, w[i], v[i])
+        pA[i] = torch.cat([_cross(w[i], h_ang) + _cross(v[i], h_lin), _cross(w[i], h_lin)], dim=1)   # cross_force_vec
+        IA[i] = _spatial_inertia(robot, i).unsqueeze(0).repeat(B, 1, 1)
+    U, d, u = [None] * N, [None] * N, [None] * N
+    for i in range(N - 1, 0, -1):
+        S = torch.cat([robot.axis[i:i + 1].expand(B, 3), zeros], dim=1)          # joint axis, zero for fixed links
+        U[i] = (IA[i] @ S.unsqueeze(2)).squeeze(2)
+        d[i] = (S * U[i]).sum(-1)
+        u[i] = -(pA[i] * S).sum(-1)
+        if robot.dof[i] >= 0:
+            u[i] = f[:, robot.dof[i]] + u[i]
+        par = robot.parent[i]
+        if par > 0:
+            Ud = U[i] / (d[i].unsqueeze(1) + 1e-37)
+            IAi = IA[i] - U[i].unsqueeze(2) @ Ud.unsqueeze(1)
+            pa = pA[i] + (IAi @ c[i].unsqueeze(2)).squeeze(2) + U[i] * (u[i] / (d[i] + 1e-37)).unsqueeze(1)
+            Rj, tj = joints[i]
+            X = _motion_matrix(Rj, tj)
+            IA[par] = IA[par] + X.transpose(-2, -1) @ IAi @ X
+            # SpatialForceVec.transform by the joint pose (sva:281-291)
+            pl = (Rj @ pa[:, 3:].unsqueeze(2)).squeeze(2)
+            pg = ((_skew(tj.expand(B, 3)) @ Rj) @ pa[:, 3:].unsqueeze(2)).squeeze(2) + (Rj @ pa[:, :3].unsqueeze(2)).squeeze(2)
+            pA[par] = pA[par] + torch.cat([pg, pl], dim=1)
+    acc = [torch.cat([zeros, g], dim=1)] + [None] * (N - 1)
+    cols = [None] * robot.n_dofs
+    for i in range(1, N):
+        Rj, tj = joints[i]
+        X = _motion_matrix(Rj, tj)                                               # transform by the inverse joint pose
+        a = (X @ acc[robot.parent[i]].unsqueeze(2)).squeeze(2) + c[i]
+        if robot.dof[i] >= 0:
+            qdd_i = (1.0 / d[i]) * (u[i] - (U[i] * a).sum(-1))
+            cols[robot.dof[i]] = qdd_i
+            a = a + torch.cat([robot.axis[i:i + 1].expand(B, 3), zeros], dim=1) * qdd_i.unsqueeze(1)
+        acc[i] = a
+    return torch.stack(cols, dim=1)
+
+
 def sample_inputs(robot, batch, seed=0, dtype=torch.float32, vel_scale=0.2, acc_scale=0.4):
     """Seeded synthetic inputs: q ~ U(joint limits), qd ~ U(+-0.2 vel_limit), qdd ~ U(+-0.4 vel_limit)
     (ranges of data_utils.py:76-98)."""
