@@ -44,6 +44,9 @@ _SIGNATURES = {
                                                          _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                          _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                                          ctypes.c_void_p, ctypes.c_void_p]),
+    "drmb200_forward_dynamics": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
+                                                _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
+                                                ctypes.c_void_p]),
     "drmb200_kinematic_state": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, ctypes.c_int64,
                                                _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "drmb200_build_link_table": (ctypes.c_int, [_c_float_p, ctypes.c_int32, _c_float_p, ctypes.c_void_p]),
@@ -149,6 +152,19 @@ def inverse_dynamics_raw(topo, table, q, qd, qdd, flags, out=None):
                                             flags, _ptr(tau), _stream())
     _check(rc, "drmb200_inverse_dynamics")
     return tau
+
+
+def forward_dynamics_raw(topo, table, q, qd, f, flags, out=None):
+    """Articulated-body algorithm, one launch (drmb200_forward_dynamics)."""
+    _require_cuda(table, q, qd, f)
+    q, qd, f = q.contiguous(), qd.contiguous(), f.contiguous()
+    B, n = q.shape
+    qdd = out if out is not None else torch.empty((B, n), device=q.device, dtype=torch.float32)
+    with torch.cuda.device(q.device):
+        rc = lib().drmb200_forward_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B,
+                                            flags, _ptr(qdd), _stream())
+    _check(rc, "drmb200_forward_dynamics")
+    return qdd
 
 
 def kinematic_state_raw(topo, table, q, qd=None, want_poses=True, want_quats=False):
@@ -273,3 +289,34 @@ class InverseDynamicsFunction(torch.autograd.Function):
                 _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_inverse_dynamics_backward")
         return table_grad, q_grad, qd_grad, qdd_grad, None, None
+
+
+class ForwardDynamicsFunction(torch.autograd.Function):
+    """(table, q, qd, f) -> qdd; articulated-body kernel forward, analytic adjoint kernel backward."""
+
+    @staticmethod
+    def forward(ctx, table, q, qd, f, topo, flags):
+        table, q, qd, f = table.contiguous(), q.contiguous(), qd.contiguous(), f.contiguous()
+        qdd = forward_dynamics_raw(topo, table, q, qd, f, flags)
+        ctx.save_for_backward(table, q, qd, f)
+        ctx.topo, ctx.flags = topo, flags
+        return qdd
+
+    @staticmethod
+    def backward(ctx, g_qdd):
+        table, q, qd, f = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        B, n = q.shape
+        g_qdd = g_qdd.contiguous()
+        _require_cuda(g_qdd)
+        table_grad = torch.zeros_like(table) if need[0] else None
+        q_grad = torch.empty_like(q) if need[1] else None
+        qd_grad = torch.empty_like(q) if need[2] else None
+        f_grad = torch.empty_like(q) if need[3] else None
+        ws = _workspace(ctx.topo, B, q.device)
+        with torch.cuda.device(q.device):
+            rc = lib().drmb200_forward_dynamics_backward(
+                ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B, ctx.flags, _ptr(g_qdd), _ptr(q_grad), _ptr(qd_grad),
+                _ptr(f_grad), _ptr(table_grad), _ptr(ws), _stream())
+        _check(rc, "drmb200_forward_dynamics_backward")
+        return table_grad, q_grad, qd_grad, f_grad, None, None

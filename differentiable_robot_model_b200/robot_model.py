@@ -296,10 +296,27 @@ class DifferentiableRobotModel(torch.nn.Module):
         include_gravity: Optional[bool] = True,
         use_damping: Optional[bool] = False,
     ) -> torch.Tensor:
-        r"""Joint accelerations under applied torques ``f``: solves ``H(q) qdd = f - nle(q, qd)``.  The reference
-        evaluates the articulated-body algorithm (``robot_model.py:488-624``); both are exact solutions of the same
-        equations of motion (the reference's own tolerance against pybullet is rtol 1e-2).  Unlike the reference this
-        does not modify ``f`` in place when ``use_damping`` is set (``robot_model.py:521``)."""
+        r"""Joint accelerations under applied joint forces ``f``: the articulated-body algorithm of
+        ``robot_model.py:488-624`` in ONE launch (``csrc/aba.cu``), with the reference's arithmetic (general 6x6
+        articulated inertias -- ``inertia_mat`` is never symmetrised --, ``+1e-37`` regularisers).  Differentiable
+        w.r.t. q, qd, f and every learnable link parameter through the analytic adjoint kernel.  Unlike the reference
+        this does not overwrite the caller's ``f`` when ``use_damping`` is set (``robot_model.py:521``)."""
+        self._check_q(q, qd, f)
+        flags = (engine.GRAVITY if include_gravity else 0) | (engine.DAMPING if use_damping else 0)
+        return engine.ForwardDynamicsFunction.apply(self._link_table(), q, qd, f, self._topology, flags)
+
+    @tensor_check
+    def compute_forward_dynamics_crba(
+        self,
+        q: torch.Tensor,
+        qd: torch.Tensor,
+        f: torch.Tensor,
+        include_gravity: Optional[bool] = True,
+        use_damping: Optional[bool] = False,
+    ) -> torch.Tensor:
+        r"""Forward dynamics as ``H(q)^-1 (f - nle(q, qd))``: n + 2 stacked RNEA evaluations (two launches) and a
+        batched ``torch.linalg.solve``.  Equal to :meth:`compute_forward_dynamics` when every ``inertia_mat`` is
+        symmetric; kept as an independent cross-check of the articulated-body kernel."""
         self._check_q(q, qd, f)
         nle = self.compute_inverse_dynamics(q, qd, torch.zeros_like(q), include_gravity, use_damping)
         H = self.compute_lagrangian_inertia_matrix(q, include_gravity=False, use_damping=False)

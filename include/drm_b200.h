@@ -16,6 +16,8 @@
  *                                        update_kinematic_state + iterative_newton_euler
  *                                        (robot_model.py:251-303) + axis projection + damping.
  *   drmb200_inverse_dynamics_backward    analytic adjoint of RNEA.
+ *   drmb200_forward_dynamics   replaces  compute_forward_dynamics (robot_model.py:488-624), the articulated-body
+ *                                        algorithm, in one launch.
  *   drmb200_fk_jacobian_host   the same FK+Jacobian op on HOST buffers (pinned or pageable):
  *                              chunked H2D -> kernel -> D2H pipeline on internal streams.
  *
@@ -133,6 +135,16 @@ int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo,
                                       const float* g_tau,
                                       float* q_grad, float* qd_grad, float* qdd_grad,
                                       float* table_grad, void* workspace, void* cuda_stream);
+
+/*
+ * Articulated-body forward dynamics, qdd [B, n_dofs] from applied joint forces f [B, n_dofs]: replaces
+ * compute_forward_dynamics (robot_model.py:488-624) in one launch, with the reference's arithmetic (general 6x6
+ * articulated inertias, U = IA S used as a column, +1e-37 regularisers).  flags = DRMB200_GRAVITY | DRMB200_DAMPING
+ * (damping: f - damping * qd is applied internally; the caller's f is NOT modified, unlike robot_model.py:521).
+ */
+int drmb200_forward_dynamics(const drmb200_topology_t* topo,
+                             const float* table, const float* q, const float* qd, const float* f,
+                             int64_t batch, uint32_t flags, float* qdd, void* cuda_stream);
 
 /*
  * World pose (and body-frame spatial velocity) of EVERY link in one launch: replaces update_kinematic_state

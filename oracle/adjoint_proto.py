@@ -256,3 +256,251 @@ def inverse_dynamics_backward(table, parent, axis, dof, q, qd, qdd, g_tau, gravi
         tg[i, 0:9] += (Mbar[i] @ Q.transpose(1, 2)).sum(0).reshape(9)
         tg[i, 9:12] += rbar[i].sum(0)
     return q_grad, qd_grad, qdd_grad, tg
+
+
+# ------------------------------------------------------------------------------------------------
+# articulated-body forward dynamics (robot_model.py:488-624) and its adjoint
+# ------------------------------------------------------------------------------------------------
+def _skew_m(r):
+    """[..., 3] -> [..., 3, 3] with skew(r) b = r x b."""
+    z = torch.zeros_like(r[..., 0])
+    return torch.stack([torch.stack([z, -r[..., 2], r[..., 1]], -1),
+                        torch.stack([r[..., 2], z, -r[..., 0]], -1),
+                        torch.stack([-r[..., 1], r[..., 0], z], -1)], -2)
+
+
+def _unskew(Sb):
+    """Adjoint of _skew_m: [..., 3, 3] -> [..., 3]."""
+    return torch.stack([Sb[..., 2, 1] - Sb[..., 1, 2], Sb[..., 0, 2] - Sb[..., 2, 0], Sb[..., 1, 0] - Sb[..., 0, 1]], -1)
+
+
+def _mv(M, x):
+    return (M @ x[:, :, None])[:, :, 0]
+
+
+def _outer(x, y):
+    return x[:, :, None] * y[:, None, :]
+
+
+ABA_EPS = 1e-37
+
+
+def forward_dynamics_with_backward(table, parent, axis, dof, q, qd, f, g_qdd, gravity=True, damping=False):
+    """The reference's articulated-body algorithm on the link table (blocks [[A, B], [C, D]] of the 6x6 articulated
+    inertia acting on [ang; lin]) followed by its hand-derived adjoint, exactly the recursions csrc/aba.cu and
+    csrc/backward_aba.cu evaluate.  Returns (qdd, q_grad, qd_grad, f_grad, table_grad)."""
+    B, n = q.shape
+    N = table.shape[0]
+    dt = q.dtype
+    z3 = torch.zeros(B, 3, dtype=dt)
+    cr = _skew_cross
+    T = lambda X: X.transpose(1, 2)  # noqa: E731
+
+    # ================================ forward ======================================================
+    J = [None] * N
+    w, v = [z3] * N, [z3] * N
+    ca, cl = [z3] * N, [z3] * N
+    hl, ha = [None] * N, [None] * N
+    A, Bm, C, D = [None] * N, [None] * N, [None] * N, [None] * N
+    p_ang, p_lin = [None] * N, [None] * N
+    for i in range(1, N):
+        P = parent[i]
+        M, F, Q, dQ, sign = _joint(table, i, axis[i], q[:, dof[i]] if axis[i] != 0 else q[:, 0])
+        r = table[i, 9:12].expand(B, 3)
+        s = _axis_vec(axis[i], dt)
+        qd_k = qd[:, dof[i]] if axis[i] != 0 else torch.zeros(B, dtype=dt)
+        wJ = qd_k[:, None] * s
+        E = T(M)
+        w[i] = _mv(E, w[P]) + wJ
+        v[i] = _mv(E, v[P] + cr(w[P], r))
+        ca[i], cl[i] = cr(w[i], wJ), cr(v[i], wJ)
+        Io, mc, m = table[i, 12:21].reshape(3, 3), table[i, 21:24].expand(B, 3), table[i, 24]
+        hl[i] = m * v[i] - cr(mc, w[i])
+        ha[i] = w[i] @ Io.T + cr(mc, v[i])
+        p_ang[i] = cr(w[i], ha[i]) + cr(v[i], hl[i])
+        p_lin[i] = cr(w[i], hl[i])
+        Smc = _skew_m(table[i, 21:24])
+        A[i] = Io.expand(B, 3, 3).clone()
+        Bm[i] = Smc.expand(B, 3, 3).clone()
+        C[i] = Smc.T.expand(B, 3, 3).clone()
+        D[i] = (m * torch.eye(3, dtype=dt)).expand(B, 3, 3).clone()
+        J[i] = (M, F, Q, dQ, sign, r, s, wJ)
+    Ua, Ul, d, u, inv = [z3] * N, [z3] * N, [None] * N, [None] * N, [None] * N
+    Ap, Bp, Cp, Dp = [None] * N, [None] * N, [None] * N, [None] * N      # IA' blocks
+    pa_ang, pa_lin = [None] * N, [None] * N
+    for i in range(N - 1, 0, -1):
+        P = parent[i]
+        M, F, Q, dQ, sign, r, s, wJ = J[i]
+        mov = axis[i] != 0
+        if mov:
+            Ua[i], Ul[i] = A[i] @ s, C[i] @ s
+            d[i] = Ua[i] @ s
+            fk = f[:, dof[i]] - (table[i, 25] * qd[:, dof[i]] if damping else 0.0)
+            u[i] = fk - p_ang[i] @ s
+        if P > 0:
+            if mov:
+                inv[i] = 1.0 / (d[i] + ABA_EPS)
+                k = inv[i][:, None, None]
+                Ap[i] = A[i] - _outer(Ua[i], Ua[i]) * k
+                Bp[i] = Bm[i] - _outer(Ua[i], Ul[i]) * k
+                Cp[i] = C[i] - _outer(Ul[i], Ua[i]) * k
+                Dp[i] = D[i] - _outer(Ul[i], Ul[i]) * k
+                ud = (u[i] * inv[i])[:, None]
+                pa_ang[i] = p_ang[i] + _mv(Ap[i], ca[i]) + _mv(Bp[i], cl[i]) + Ua[i] * ud
+                pa_lin[i] = p_lin[i] + _mv(Cp[i], ca[i]) + _mv(Dp[i], cl[i]) + Ul[i] * ud
+            else:
+                Ap[i], Bp[i], Cp[i], Dp[i] = A[i], Bm[i], C[i], D[i]
+                pa_ang[i], pa_lin[i] = p_ang[i], p_lin[i]
+            S = _skew_m(r)
+            Ah, Bh, Ch, Dh = (M @ X @ T(M) for X in (Ap[i], Bp[i], Cp[i], Dp[i]))
+            D[P] = D[P] + Dh
+            Bm[P] = Bm[P] + Bh + S @ Dh
+            C[P] = C[P] + Ch - Dh @ S
+            A[P] = A[P] + Ah + S @ Ch - Bh @ S - S @ Dh @ S
+            Ql = _mv(M, pa_lin[i])
+            p_lin[P] = p_lin[P] + Ql
+            p_ang[P] = p_ang[P] + cr(r, Ql) + _mv(M, pa_ang[i])
+    al, a = [z3] * N, [z3] * N
+    alq, aq = [z3] * N, [z3] * N          # a' (before the joint acceleration is added)
+    a[0] = torch.tensor([0.0, 0.0, 9.81 if gravity else 0.0], dtype=dt).expand(B, 3)
+    qdd = torch.zeros(B, n, dtype=dt)
+    for i in range(1, N):
+        P = parent[i]
+        M, F, Q, dQ, sign, r, s, wJ = J[i]
+        E = T(M)
+        alq[i] = _mv(E, al[P]) + ca[i]
+        aq[i] = _mv(E, a[P] + cr(al[P], r)) + cl[i]
+        al[i], a[i] = alq[i], aq[i]
+        if axis[i] != 0:
+            qdd_i = (1.0 / d[i]) * (u[i] - ((Ua[i] * alq[i]).sum(1) + (Ul[i] * aq[i]).sum(1)))
+            qdd[:, dof[i]] = qdd_i
+            al[i] = alq[i] + qdd_i[:, None] * s
+
+    # ================================ adjoint ======================================================
+    q_grad, qd_grad, f_grad = (torch.zeros(B, n, dtype=dt) for _ in range(3))
+    tg = torch.zeros(N, 28, dtype=dt)
+    Mbar = [torch.zeros(B, 3, 3, dtype=dt) for _ in range(N)]
+    rbar = [torch.zeros(B, 3, dtype=dt) for _ in range(N)]
+    Z = lambda: torch.zeros(B, 3, dtype=dt)  # noqa: E731
+    alb, ab = [Z() for _ in range(N)], [Z() for _ in range(N)]
+    cab, clb = [Z() for _ in range(N)], [Z() for _ in range(N)]
+    Uab, Ulb = [Z() for _ in range(N)], [Z() for _ in range(N)]
+    db = [torch.zeros(B, dtype=dt) for _ in range(N)]
+    ub = [torch.zeros(B, dtype=dt) for _ in range(N)]
+
+    # ---- reverse of pass 3 (leaves -> root) -----------------------------------------------------------
+    for i in range(N - 1, 0, -1):
+        P = parent[i]
+        M, F, Q, dQ, sign, r, s, wJ = J[i]
+        alq_b, aq_b = alb[i], ab[i]
+        if axis[i] != 0:
+            qb = g_qdd[:, dof[i]] + alb[i] @ s
+            k = (qb / d[i])[:, None]
+            ub[i] = ub[i] + qb / d[i]
+            Uab[i] = Uab[i] - k * alq[i]
+            Ulb[i] = Ulb[i] - k * aq[i]
+            db[i] = db[i] - qb * qdd[:, dof[i]] / d[i]
+            alq_b = alb[i] - k * Ua[i]
+            aq_b = ab[i] - k * Ul[i]
+        cab[i] = cab[i] + alq_b
+        clb[i] = clb[i] + aq_b
+        ua = _mv(M, aq_b)
+        ab[P] = ab[P] + ua
+        alb[P] = alb[P] + cr(r, ua) + _mv(M, alq_b)
+        rbar[i] = rbar[i] + cr(ua, al[P])
+        Mbar[i] = Mbar[i] + _outer(a[P] + cr(al[P], r), aq_b) + _outer(al[P], alq_b)
+
+    # ---- reverse of pass 2 (root -> leaves) -----------------------------------------------------------
+    ZM = lambda: torch.zeros(B, 3, 3, dtype=dt)  # noqa: E731
+    Ab, Bb, Cb, Db = [ZM() for _ in range(N)], [ZM() for _ in range(N)], [ZM() for _ in range(N)], [ZM() for _ in range(N)]
+    pb_ang, pb_lin = [Z() for _ in range(N)], [Z() for _ in range(N)]
+    for i in range(1, N):
+        P = parent[i]
+        M, F, Q, dQ, sign, r, s, wJ = J[i]
+        mov = axis[i] != 0
+        if P > 0:
+            E = T(M)
+            # force transform
+            Qa_b, Ql_b = pb_ang[P], pb_lin[P]
+            t = Ql_b + cr(Qa_b, r)
+            pal_b, paa_b = _mv(E, t), _mv(E, Qa_b)
+            Ql = _mv(M, pa_lin[i])
+            rbar[i] = rbar[i] + cr(Ql, Qa_b)
+            Mbar[i] = Mbar[i] + _outer(t, pa_lin[i]) + _outer(Qa_b, pa_ang[i])
+            # Y = T^T (rotated) T
+            S = _skew_m(r)
+            Ah, Bh, Ch, Dh = (M @ X @ T(M) for X in (Ap[i], Bp[i], Cp[i], Dp[i]))
+            YA, YB, YC, YD = Ab[P], Bb[P], Cb[P], Db[P]
+            Ah_b = YA
+            Bh_b = YB + YA @ S
+            Ch_b = YC - S @ YA
+            Dh_b = YD - S @ YB + YC @ S - S @ YA @ S
+            Sb = YB @ T(Dh) - T(Dh) @ YC + YA @ T(Ch) - T(Bh) @ YA + YA @ S @ T(Dh) + T(Dh) @ S @ YA
+            rbar[i] = rbar[i] + _unskew(Sb)
+            # rotation blocks
+            Ap_b, Bp_b, Cp_b, Dp_b = (E @ X @ M for X in (Ah_b, Bh_b, Ch_b, Dh_b))
+            for Xb, X in ((Ah_b, Ap[i]), (Bh_b, Bp[i]), (Ch_b, Cp[i]), (Dh_b, Dp[i])):
+                Mbar[i] = Mbar[i] + Xb @ M @ T(X) + T(Xb) @ M @ X
+            pb_ang[i] = pb_ang[i] + paa_b
+            pb_lin[i] = pb_lin[i] + pal_b
+            if mov:
+                k = inv[i]
+                Ap_b = Ap_b + _outer(paa_b, ca[i]); Bp_b = Bp_b + _outer(paa_b, cl[i])
+                Cp_b = Cp_b + _outer(pal_b, ca[i]); Dp_b = Dp_b + _outer(pal_b, cl[i])
+                cab[i] = cab[i] + _mv(T(Ap[i]), paa_b) + _mv(T(Cp[i]), pal_b)
+                clb[i] = clb[i] + _mv(T(Bp[i]), paa_b) + _mv(T(Dp[i]), pal_b)
+                sig = (Ua[i] * paa_b).sum(1) + (Ul[i] * pal_b).sum(1)
+                Uab[i] = Uab[i] + paa_b * (u[i] * k)[:, None]
+                Ulb[i] = Ulb[i] + pal_b * (u[i] * k)[:, None]
+                ub[i] = ub[i] + sig * k
+                inv_b = sig * u[i]
+                Uab[i] = Uab[i] - k[:, None] * (_mv(Ap_b, Ua[i]) + _mv(T(Ap_b), Ua[i]) + _mv(Bp_b, Ul[i]) + _mv(T(Cp_b), Ul[i]))
+                Ulb[i] = Ulb[i] - k[:, None] * (_mv(T(Bp_b), Ua[i]) + _mv(Cp_b, Ua[i]) + _mv(Dp_b, Ul[i]) + _mv(T(Dp_b), Ul[i]))
+                inv_b = inv_b - ((Ua[i] * _mv(Ap_b, Ua[i])).sum(1) + (Ua[i] * _mv(Bp_b, Ul[i])).sum(1)
+                                 + (Ul[i] * _mv(Cp_b, Ua[i])).sum(1) + (Ul[i] * _mv(Dp_b, Ul[i])).sum(1))
+                db[i] = db[i] - inv_b * k * k
+            Ab[i] = Ab[i] + Ap_b; Bb[i] = Bb[i] + Bp_b; Cb[i] = Cb[i] + Cp_b; Db[i] = Db[i] + Dp_b
+        if mov:
+            f_grad[:, dof[i]] = ub[i]
+            if damping:
+                qd_grad[:, dof[i]] += -table[i, 25] * ub[i]
+                tg[i, 25] += -(ub[i] * qd[:, dof[i]]).sum()
+            pb_ang[i] = pb_ang[i] - ub[i][:, None] * s
+            Uab[i] = Uab[i] + db[i][:, None] * s
+            Ab[i] = Ab[i] + _outer(Uab[i], s.expand(B, 3))
+            Cb[i] = Cb[i] + _outer(Ulb[i], s.expand(B, 3))
+        # rigid-body inertia IA0 = [[Io, mc^], [mc^T, m 1]]
+        tg[i, 12:21] += Ab[i].sum(0).reshape(9)
+        tg[i, 21:24] += _unskew(Bb[i] + T(Cb[i])).sum(0)
+        tg[i, 24] += (Db[i][:, 0, 0] + Db[i][:, 1, 1] + Db[i][:, 2, 2]).sum()
+
+    # ---- reverse of pass 1 (leaves -> root) -----------------------------------------------------------
+    wb, vb = [Z() for _ in range(N)], [Z() for _ in range(N)]
+    for i in range(N - 1, 0, -1):
+        P = parent[i]
+        M, F, Q, dQ, sign, r, s, wJ = J[i]
+        Io, mc, m = table[i, 12:21].reshape(3, 3), table[i, 21:24].expand(B, 3), table[i, 24]
+        pi_, rho = pb_ang[i], pb_lin[i]
+        wb[i] = wb[i] + cr(ha[i], pi_) + cr(hl[i], rho)
+        vb[i] = vb[i] + cr(hl[i], pi_)
+        hab = cr(pi_, w[i])
+        hlb = cr(pi_, v[i]) + cr(rho, w[i])
+        vb[i] = vb[i] + m * hlb + cr(hab, mc)
+        wb[i] = wb[i] + cr(mc, hlb) + hab @ Io
+        tg[i, 24] += (hlb * v[i]).sum()
+        tg[i, 21:24] += (cr(hlb, w[i]) + cr(v[i], hab)).sum(0)
+        tg[i, 12:21] += _outer(hab, w[i]).sum(0).reshape(9)
+        wb[i] = wb[i] + cr(wJ, cab[i])
+        vb[i] = vb[i] + cr(wJ, clb[i])
+        wJb = cr(cab[i], w[i]) + cr(clb[i], v[i]) + wb[i]
+        uv = _mv(M, vb[i])
+        vb[P] = vb[P] + uv
+        wb[P] = wb[P] + cr(r, uv) + _mv(M, wb[i])
+        rbar[i] = rbar[i] + cr(uv, w[P])
+        Mbar[i] = Mbar[i] + _outer(v[P] + cr(w[P], r), vb[i]) + _outer(w[P], wb[i])
+        if axis[i] != 0:
+            qd_grad[:, dof[i]] += wJb @ s
+            q_grad[:, dof[i]] = sign * ((T(F) @ Mbar[i]) * dQ).sum((1, 2))
+        tg[i, 0:9] += (Mbar[i] @ T(Q)).sum(0).reshape(9)
+        tg[i, 9:12] += rbar[i].sum(0)
+    return qdd, q_grad, qd_grad, f_grad, tg

@@ -79,3 +79,37 @@ def test_forward_dynamics_gradients_match_reference_autograd(robot_stem, tag):
         assert_close(mine[int(idx)].reshape(ref.shape).numpy(), ref, rtol=2e-3, atol=2e-4 * max(fam, 1e-6), what=key)
         checked += 1
     assert checked > 0
+
+
+@pytest.mark.parametrize("stem", ["2link_robot", "iiwa7", "panda", "trifinger_edu", "iiwa7_allegro"])
+def test_forward_dynamics_adjoint_recursions_match_autograd(stem):
+    """The hand-derived adjoint of the articulated-body algorithm (oracle/adjoint_proto.py -- the recursions the
+    CUDA backward kernel evaluates) against torch.autograd of the oracle, fp64, non-symmetric inertias."""
+    from oracle import adjoint_proto as AP
+    dt = torch.float64
+    robot = O.load_robot(urdf_path(stem), dt)
+    gen = torch.Generator().manual_seed(11)
+    scale = robot.inertia.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-6)
+    robot.inertia = robot.inertia + 0.05 * scale * torch.randn(robot.inertia.shape, generator=gen, dtype=dt)
+    q, qd, _ = O.sample_inputs(robot, 4, seed=3, dtype=dt)
+    f = torch.randn(4, robot.n_dofs, generator=gen, dtype=dt)
+    G = torch.randn(4, robot.n_dofs, generator=gen, dtype=dt)
+    table = O.link_table(robot).to(dt)
+    qg, qdg, fg = (t.clone().requires_grad_(True) for t in (q, qd, f))
+    names = ("trans", "rpy", "mass", "com", "inertia", "damping")
+    for name in names:
+        setattr(robot, name, getattr(robot, name).detach().clone().requires_grad_(True))
+    params = [getattr(robot, name) for name in names]
+    for grav, damp in ((True, True), (False, False)):
+        qdd_o = O.forward_dynamics(robot, qg, qdg, fg, grav, damp)
+        want = torch.autograd.grad((G * qdd_o).sum(), [qg, qdg, fg] + params, allow_unused=True)
+        qdd, dq, dqd, df, tg = AP.forward_dynamics_with_backward(table, robot.parent, O.axis_codes(robot), robot.dof,
+                                                                 q, qd, f, G, grav, damp)
+        got_params = torch.autograd.grad((O.link_table(robot) * tg).sum(), params, allow_unused=True)
+        rel = lambda a, b: float((a - b).abs().max() / (b.abs().max() + 1e-300))  # noqa: E731
+        assert rel(qdd, qdd_o.detach()) < 1e-12
+        for a, b in zip((dq, dqd, df) + tuple(got_params), want):
+            if b is None:
+                continue
+            a = torch.zeros_like(b) if a is None else a
+            assert rel(a, b) < 1e-9, (stem, grav, damp)
