@@ -206,7 +206,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
 
 int64_t table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch) {
     if (topo == nullptr || topo->n_links < 1 || topo->n_links > DRMB200_MAX_LINKS) return 0;
-    int64_t tiles = (batch + 31) / 32;            // smallest tile the launchers may pick
+    int64_t tiles = (batch + 15) / 16;            // smallest tile the launchers may pick (backward_aba.cu)
     if (tiles < 1) tiles = 1;
     const int64_t grid = tiles < BWD_MAX_GRID ? tiles : BWD_MAX_GRID;
     return grid * topo->n_links * DRMB200_TABLE_STRIDE * (int64_t)sizeof(float);

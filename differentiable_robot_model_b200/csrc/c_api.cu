@@ -59,6 +59,8 @@ int inverse_dynamics_backward_device(const drmb200_topology_t*, const float*, co
                                      float*, void*, cudaStream_t);
 int forward_dynamics_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*,
                             int64_t, uint32_t, float*, cudaStream_t);
+int forward_dynamics_backward_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*,
+                                     int64_t, uint32_t, const float*, float*, float*, float*, float*, void*, cudaStream_t);
 int64_t table_grad_workspace_bytes(const drmb200_topology_t*, int64_t);
 int build_table_device(const float*, int32_t, float*, cudaStream_t);
 int kinematic_state_device(const drmb200_topology_t*, const float*, const float*, const float*, int64_t, float*, float*,
@@ -213,6 +215,14 @@ int drmb200_forward_dynamics(const drmb200_topology_t* topo, const float* table,
                              const float* f, int64_t batch, uint32_t flags, float* qdd, void* cuda_stream) {
     return drm::forward_dynamics_device(topo, table, q, qd, f, batch, flags, qdd,
                                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_forward_dynamics_backward(const drmb200_topology_t* topo, const float* table, const float* q,
+                                      const float* qd, const float* f, int64_t batch, uint32_t flags,
+                                      const float* g_qdd, float* q_grad, float* qd_grad, float* f_grad,
+                                      float* table_grad, void* workspace, void* cuda_stream) {
+    return drm::forward_dynamics_backward_device(topo, table, q, qd, f, batch, flags, g_qdd, q_grad, qd_grad, f_grad,
+                                                 table_grad, workspace, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int drmb200_kinematic_state(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,

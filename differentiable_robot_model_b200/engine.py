@@ -47,6 +47,10 @@ _SIGNATURES = {
     "drmb200_forward_dynamics": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                 ctypes.c_void_p]),
+    "drmb200_forward_dynamics_backward": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
+                                                         _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
+                                                         _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                         ctypes.c_void_p, ctypes.c_void_p]),
     "drmb200_kinematic_state": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, ctypes.c_int64,
                                                _c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p]),
     "drmb200_build_link_table": (ctypes.c_int, [_c_float_p, ctypes.c_int32, _c_float_p, ctypes.c_void_p]),

@@ -147,6 +147,18 @@ int drmb200_forward_dynamics(const drmb200_topology_t* topo,
                              int64_t batch, uint32_t flags, float* qdd, void* cuda_stream);
 
 /*
+ * Adjoint of drmb200_forward_dynamics given g_qdd [B, n_dofs] (the reference differentiates its op graph with
+ * autograd; this is the analytic reverse-mode recursion, exact also for non-symmetric inertia matrices).  Any of
+ * q_grad / qd_grad / f_grad [B, n_dofs] and table_grad [n_links, 28] may be NULL; table_grad is accumulated into and
+ * needs `workspace` of drmb200_table_grad_workspace_bytes() bytes.
+ */
+int drmb200_forward_dynamics_backward(const drmb200_topology_t* topo,
+                                      const float* table, const float* q, const float* qd, const float* f,
+                                      int64_t batch, uint32_t flags, const float* g_qdd,
+                                      float* q_grad, float* qd_grad, float* f_grad,
+                                      float* table_grad, void* workspace, void* cuda_stream);
+
+/*
  * World pose (and body-frame spatial velocity) of EVERY link in one launch: replaces update_kinematic_state
  * (robot_model.py:140-195) and, with `quats`, compute_forward_kinematics_all_links (robot_model.py:198-221).
  * Outputs are link-major / component-major so that stores coalesce:
