@@ -108,6 +108,26 @@ __device__ __forceinline__ M3 conj_b(const M3& M, const M3& Y) { return mulNT(mu
 __device__ __forceinline__ M3 conjT_b(const M3& M, const M3& Y) { return mul(mulTN(M, Y), M); }    // M^T Y M
 __device__ __forceinline__ float quad(V3 x, const M3& Y, V3 y) { return dot(x, mul(Y, y)); }       // x^T Y y
 
+// Sum of NV <= 32 per-thread values over the (single-warp) CTA into acc_row[0..NV): transposed through a padded
+// scratch so that lane j adds up value j of all 32 threads -- 32 independent short chains instead of NV serial
+// shuffle trees (the kernel runs at 2-3 warps per SM, latency is what it pays for).  Fixed order: deterministic.
+template <int NV>
+__device__ __forceinline__ void warp_accumulate(float* scratch, float* acc_row, const float (&vals)[NV], bool active) {
+    static_assert(NV <= 32, "one lane per value");
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) scratch[j * 33 + lane] = active ? vals[j] : 0.f;
+    __syncwarp();
+    if (lane < NV) {
+        const float* row = scratch + lane * 33;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) { s0 += row[c]; s1 += row[c + 1]; s2 += row[c + 2]; s3 += row[c + 3]; }
+        acc_row[lane] += (s0 + s1) + (s2 + s3);
+    }
+    __syncwarp();
+}
+
 struct Blocks { M3 A, B, C, D; };
 __device__ __forceinline__ Blocks ld_blocks(const float* p, int T) {
     Blocks b;
@@ -122,6 +142,7 @@ template <bool NEED_TABLE, int T>
 __global__ void __launch_bounds__(T < 32 ? 32 : T)
 aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs args) {
     constexpr int TB = T < 32 ? 32 : T;
+    static_assert(TB == 32, "warp_accumulate assumes a single-warp CTA");
     extern __shared__ __align__(128) float smem[];
     const int n = prog.n_dofs, N = prog.n_links;
     const AbaBwdSmem L(T, n, N);
@@ -328,7 +349,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 m3_to_array(Mbar, vals);
                 const V3 rbar = cross(ua, alp);
                 vals[9] = rbar.x; vals[10] = rbar.y; vals[11] = rbar.z;
-                block_accumulate<12, TB>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active, [](int j) { return j; });
+                warp_accumulate<12>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active);
             }
         }
 
@@ -453,7 +474,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 const V3 mcb = unskew(madd(Ib.B, transpose(Ib.C)));                 // B = mc^, C = (mc^)^T
                 vals[21] = mcb.x; vals[22] = mcb.y; vals[23] = mcb.z;
                 vals[24] = Ib.D.a00 + Ib.D.a11 + Ib.D.a22;
-                block_accumulate<26, TB>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active, [](int j) { return j; });
+                warp_accumulate<26>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active);
             }
         }
 
@@ -508,7 +529,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 const V3 mcb = cross_add(hlb, w, cross(v, hab));
                 vals[21] = mcb.x; vals[22] = mcb.y; vals[23] = mcb.z;
                 vals[24] = dot(hlb, v);
-                block_accumulate<25, TB>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active, [](int j) { return j; });
+                warp_accumulate<25>(s_scr, s_acc + i * DRMB200_TABLE_STRIDE, vals, active);
             }
         }
 

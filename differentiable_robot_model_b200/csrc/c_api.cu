@@ -14,7 +14,7 @@ namespace drm {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-static std::atomic<int> g_options[4] = {{-1}, {-1}, {-1}, {-1}};   // 0: fk_variant, 1: fk_tile, 2: fk_unroll, 3: fk_packed
+static std::atomic<int> g_options[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};   // 0: fk_variant, 1: fk_tile, 2: fk_unroll, 3: fk_packed, 4: rnea_packed
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -34,11 +34,13 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 //                  flight, 19.8 vs 21.0 at 2^22); for the 16-DoF Allegro hand, whose even row strides make every J-tile
 //                  access a 16-way bank conflict, touching the tile once per column wins (9.8 vs 6.3 G cfg/s).
 //   3 "fk_packed"  (DRMB200_FK_PACKED):  1 = packed FP32x2 (FFMA2) arithmetic in the rolled chain walk (default), 0 = scalar
+//   4 "rnea_packed" (DRMB200_RNEA_PACKED): 1 = packed FP32x2 arithmetic in the RNEA kernel (default), 0 = scalar
 int get_option(int which) {
     int v = g_options[which].load(std::memory_order_relaxed);
     if (v < 0) {
-        static const char* names[4] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL", "DRMB200_FK_PACKED"};
-        static const int defaults[4] = {1, 0, 2, 1};
+        static const char* names[5] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL", "DRMB200_FK_PACKED",
+                                       "DRMB200_RNEA_PACKED"};
+        static const int defaults[5] = {1, 0, 2, 1, 1};
         const char* e = getenv(names[which]);
         v = e ? atoi(e) : defaults[which];
         g_options[which].store(v, std::memory_order_relaxed);
@@ -174,6 +176,7 @@ int drmb200_set_option(const char* name, int value) {
     if (name != nullptr && std::string(name) == "fk_tile") { drm::g_options[1].store(value); return DRMB200_OK; }
     if (name != nullptr && std::string(name) == "fk_unroll") { drm::g_options[2].store(value); return DRMB200_OK; }
     if (name != nullptr && std::string(name) == "fk_packed") { drm::g_options[3].store(value); return DRMB200_OK; }
+    if (name != nullptr && std::string(name) == "rnea_packed") { drm::g_options[4].store(value); return DRMB200_OK; }
     drm::set_error("unknown option");
     return DRMB200_EINVAL;
 }

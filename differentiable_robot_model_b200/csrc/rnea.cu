@@ -52,7 +52,7 @@ struct RneaSmemLayout {
         q = o;   o += RNEA_TILE * n;
         qd = o;  o += RNEA_TILE * n;
         qdd = o; o += RNEA_TILE * n;
-        tau = o; o += RNEA_TILE * n;
+        tau = qdd;                                        // qdd is dead after pass 1: tau is written over it
         table = o; o += n_links * DRMB200_TABLE_STRIDE;
         link = o;  o += n_links * 8 * RNEA_TILE;          // per link: f(3) n(3) cos sin, slot-major
         slots = o; o += n_slots * 12 * RNEA_TILE;         // branch-point motion states
@@ -60,7 +60,7 @@ struct RneaSmemLayout {
     }
 };
 
-template <int T>
+template <int T, bool PACKED>
 __global__ void __launch_bounds__(T)
 rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
     extern __shared__ __align__(128) float smem[];
@@ -115,8 +115,68 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
         const bool damp = (args.flags & DRMB200_DAMPING) != 0;
 
         // ---- pass 1: root -> leaves, motion state + body wrench ------------------------------------
-        V3 w = v3(0.f, 0.f, 0.f), v = w, al = w, a = w;     // state of the previously processed link
+        // Packed FP32x2 arithmetic (drm_common.cuh): the velocity-level and the acceleration-level quantities obey the
+        // same linear maps, so they travel as PAIRS -- W = (w | al), V = (v | a) -- and every 3x3 product, cross
+        // product with r and spatial-inertia product is one FFMA2 per two scalar FMAs.
+        const V3 zero = v3(0.f, 0.f, 0.f);
+        V3P W = pk3(zero, zero), V = W;                     // state of the previously processed link
         for (int i = 1; i < N; ++i) {
+            if (PACKED) {
+                const uint32_t row = a_tab + i * (DRMB200_TABLE_STRIDE * 4);
+                LinkRow C;
+                load_Fr_s(row, C.F, C.r);
+                {
+                    const float4 d = lds_f32x4(row + 48), e = lds_f32x4(row + 64), f = lds_f32x4(row + 80), gg = lds_f32x4(row + 96);
+                    C.Io.a00 = d.x; C.Io.a01 = d.y; C.Io.a02 = d.z; C.Io.a10 = d.w; C.Io.a11 = e.x; C.Io.a12 = e.y;
+                    C.Io.a20 = e.z; C.Io.a21 = e.w; C.Io.a22 = f.x;
+                    C.mc = v3(f.y, f.z, f.w);
+                    C.m = gg.x; C.d = gg.y;
+                }
+                const int src = prog.psrc[i];
+                V3P Wp, Vp;
+                if (src == 0) { Wp = W; Vp = V; }
+                else if (src < 0) { Wp = pk3(zero, zero); Vp = pk3(zero, v3(0.f, 0.f, g)); }
+                else {
+                    const uint32_t sl = a_slot + (src - 1) * 12 * E;
+                    Wp = pk3(ldv_s(sl), ldv_s(sl + 6 * E)); Vp = pk3(ldv_s(sl + 3 * E), ldv_s(sl + 9 * E));
+                }
+                // E x = Rz^T (F~^T x): velocities (robot_model.py:183-193), accelerations (robot_model.py:269-277)
+                W = mulT_p(C.F, Wp);
+                V = mulT_p(C.F, cross_add_p(Wp, C.r, Vp));
+                const int c = prog.dof[i];
+                float cs = 1.f, sn = 0.f, qd_k = 0.f, qdd_k = 0.f;
+                if (c >= 0) {
+                    qd_k = lds_f32(a_qd + 4u * c); qdd_k = lds_f32(a_qdd + 4u * c);
+                    sincos_pi2(lds_f32(a_q + 4u * c), sn, cs);
+                }
+                // one code path for fixed links too (cs = 1, sn = 0, zero rates are exact no-ops): only four scalars
+                // cross the branch above, the packed state is never shuffled at a join
+                W = rotzT_p(W, cs, sn);
+                V = rotzT_p(V, cs, sn);
+                V3 w, al, v, a;
+                upk3(W, w, al); upk3(V, v, a);
+                w.z += qd_k;
+                al.x = fmaf(w.y, qd_k, al.x); al.y = fmaf(-w.x, qd_k, al.y); al.z += qdd_k;         // + w x (0,0,qd) + (0,0,qdd)
+                a.x = fmaf(v.y, qd_k, a.x); a.y = fmaf(-v.x, qd_k, a.y);                            // + v x (0,0,qd)
+                W = pk3(w, al); V = pk3(v, a);
+                // body wrench (robot_model.py:289-293; spatial_vector_algebra.py:321-338), both lanes at once
+                V3 hl_v, hl_a, ha_v, ha_a;
+                upk3(inertia_lin_p(C.m, C.mc, W, V), hl_v, hl_a);
+                upk3(inertia_ang_p(C.Io, C.mc, W, V), ha_v, ha_a);
+                const V3 f = cross_add(w, hl_v, hl_a);
+                const V3 nn = cross_add(w, ha_v, cross_add(v, hl_v, ha_a));
+                const uint32_t lk = a_link + i * 8 * E;
+                stv_s(lk, f); stv_s(lk + 3 * E, nn);
+                sts_f32(lk + 6 * E, cs); sts_f32(lk + 7 * E, sn);
+                const int sv = prog.save[i];
+                if (sv >= 0) {
+                    const uint32_t sl = a_slot + sv * 12 * E;
+                    stv_s(sl, w); stv_s(sl + 3 * E, v); stv_s(sl + 6 * E, al); stv_s(sl + 9 * E, a);
+                }
+                continue;
+            }
+            V3 w, al, v, a;
+            upk3(W, w, al); upk3(V, v, a);
             const uint32_t row = a_tab + i * (DRMB200_TABLE_STRIDE * 4);
             LinkRow C;
             load_Fr_s(row, C.F, C.r);
@@ -164,6 +224,7 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
                 const uint32_t sl = a_slot + sv * 12 * E;
                 stv_s(sl, w); stv_s(sl + 3 * E, v); stv_s(sl + 6 * E, al); stv_s(sl + 9 * E, a);
             }
+            W = pk3(w, al); V = pk3(v, a);
         }
 
         // ---- pass 2: leaves -> root, wrench propagation + joint torques (robot_model.py:284-301, 353-373)
@@ -183,8 +244,14 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
                 M3 F; V3 r;
                 load_Fr_s(row, F, r);
                 const float cs = lds_f32(lk + 6 * E), sn = lds_f32(lk + 7 * E);
-                const V3 fp = mul(F, rotz(f, cs, sn));              // M f = F~ (Rz f)  (sva:281-291)
-                const V3 np = cross_add(r, fp, mul(F, rotz(nn, cs, sn)));
+                V3 fp, np;
+                if (PACKED) {                                       // (M f | M n) = F~ (Rz (f | n))  (sva:281-291)
+                    upk3(mul_pv(F, rotz_p(pk3(f, nn), cs, sn)), fp, np);
+                    np = cross_add(r, fp, np);
+                } else {
+                    fp = mul(F, rotz(f, cs, sn));
+                    np = cross_add(r, fp, mul(F, rotz(nn, cs, sn)));
+                }
                 const uint32_t pk = a_link + p * 8 * E;
                 stv_s(pk, ldv_s(pk) + fp);
                 stv_s(pk + 3 * E, ldv_s(pk + 3 * E) + np);
@@ -280,19 +347,25 @@ int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     const RneaSmemLayout L(tile, prog.n_dofs, prog.n_links, prog.n_slots);
     const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
-    static size_t configured_by_dev[2][64] = {{0}};
+    const bool packed = get_option(4) != 0;             // "rnea_packed": FP32x2 arithmetic (default) vs scalar, for A/B runs
+    static size_t configured_by_dev[4][64] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
-    size_t& configured = configured_by_dev[tile == 64 ? 0 : 1][dev & 63];
+    size_t& configured = configured_by_dev[(tile == 64 ? 0 : 1) + (packed ? 2 : 0)][dev & 63];
+    const void* kern = tile == 64 ? (packed ? (const void*)rnea_kernel<64, true> : (const void*)rnea_kernel<64, false>)
+                                  : (packed ? (const void*)rnea_kernel<128, true> : (const void*)rnea_kernel<128, false>);
     if (smem_bytes > configured) {
-        cudaError_t e = tile == 64
-            ? cudaFuncSetAttribute(rnea_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)
-            : cudaFuncSetAttribute(rnea_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
         configured = smem_bytes;
     }
-    if (tile == 64) rnea_kernel<64><<<(unsigned)tiles, 64, smem_bytes, stream>>>(prog, args);
-    else rnea_kernel<128><<<(unsigned)tiles, 128, smem_bytes, stream>>>(prog, args);
+    if (tile == 64) {
+        if (packed) rnea_kernel<64, true><<<(unsigned)tiles, 64, smem_bytes, stream>>>(prog, args);
+        else rnea_kernel<64, false><<<(unsigned)tiles, 64, smem_bytes, stream>>>(prog, args);
+    } else {
+        if (packed) rnea_kernel<128, true><<<(unsigned)tiles, 128, smem_bytes, stream>>>(prog, args);
+        else rnea_kernel<128, false><<<(unsigned)tiles, 128, smem_bytes, stream>>>(prog, args);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("rnea launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();

@@ -94,6 +94,54 @@ def bench_rnea(stem_cls, batch):
             "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK}
 
 
+def bench_forward_dynamics(stem_cls, batch):
+    """Articulated-body kernel (forward) and its adjoint kernel (input gradients / input + table gradients)."""
+    import ctypes
+    m = stem_cls(device=DEV)
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    n = robot.n_dofs
+    sets = [tuple(t.to(DEV) for t in O.sample_inputs(robot, batch, seed=r)) for r in range(min(rotate_count(batch * 16 * n), 8))]
+    fs = [torch.randn(batch, n, device=DEV) for _ in sets]
+    outs = [torch.empty(batch, n, device=DEV) for _ in sets]
+    table, topo = m._link_table(), m._topology
+    K = len(sets)
+    ms = timed(lambda i: engine.forward_dynamics_raw(topo, table, sets[i % K][0], sets[i % K][1], fs[i % K], 3, out=outs[i % K]),
+               200 if batch <= (1 << 17) else 20)
+    res = {"batch": batch, "forward_ms": ms, "forward_configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": 16 * n,
+           "forward_achieved_GBps": batch * 16 * n / ms / 1e6}
+    g = torch.randn(batch, n, device=DEV)
+    qg, qdg, fg, tg = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g), torch.zeros_like(table)
+    ws = engine._workspace(topo, batch, DEV)
+    lib, P, S = engine.lib(), engine._ptr, engine._stream
+
+    def bwd(with_table):
+        rc = lib.drmb200_forward_dynamics_backward(ctypes.byref(topo), P(table), P(sets[0][0]), P(sets[0][1]), P(fs[0]), batch, 3,
+                                                   P(g), P(qg), P(qdg), P(fg), P(tg) if with_table else None, P(ws), S())
+        assert rc == 0
+
+    for name, wt in (("backward_inputs_ms", False), ("backward_inputs_and_table_ms", True)):
+        res[name] = timed(lambda i: bwd(wt), 10)
+    if batch <= 65536:
+        # CPU baseline beside it: the torch port of the reference's articulated-body algorithm (oracle), bounded sample
+        import time
+        rows = 4096
+        cq, cqd, cf = sets[0][0][:rows].cpu(), sets[0][1][:rows].cpu(), fs[0][:rows].cpu()
+        best = 0.0
+        for threads in (8, 32, os.cpu_count() or 8):
+            torch.set_num_threads(threads)
+            with torch.no_grad():
+                O.forward_dynamics(robot, cq, cqd, cf, True, True)
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    O.forward_dynamics(robot, cq, cqd, cf, True, True)
+                rate = 3 * rows / (time.perf_counter() - t0)
+            if rate > best:
+                best, res["cpu_port_threads"] = rate, threads
+        res["cpu_port_configs_per_s"] = best
+        res["cpu_port_sample"] = f"{rows} rows x 3 calls, torch CPU port of robot_model.py:488-624"
+    return res
+
+
 def bench_fk(model, link, batch):
     robot = O.load_robot(model.urdf_path if hasattr(model, "urdf_path") else model._urdf_path, torch.float32)
     n = robot.n_dofs
@@ -178,6 +226,9 @@ def main():
     out = {"peak_GBps": PEAK, "gpu": torch.cuda.get_device_name(0)}
     out["config3_panda_rnea"] = [bench_rnea(drm.DifferentiableFrankaPanda, b) for b in (65536, 1 << 21)]
     out["kuka_rnea"] = [bench_rnea(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 21)]
+    engine.set_option("rnea_packed", 0)
+    out["kuka_rnea_scalar_arithmetic"] = [bench_rnea(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 21)]
+    engine.set_option("rnea_packed", 1)
     allegro = drm.DifferentiableRobotModel(os.path.join(drm.robot_model.robot_description_folder,
                                                         "allegro/urdf/allegro_hand_description_left.urdf"), device=DEV)
     allegro.urdf_path = allegro._urdf_model and os.path.join(drm.robot_model.robot_description_folder,
@@ -185,6 +236,7 @@ def main():
     out["config4_allegro_fk_jac"] = [bench_fk(allegro, "link_15.0_tip", b) for b in (32768, 1 << 21)]
     out["config5_kuka_train_step"] = [bench_train_step(b) for b in (131072,)]
     out["kuka_backward_kernels"] = [bench_backward_kernels(131072)]
+    out["kuka_forward_dynamics"] = [bench_forward_dynamics(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 20)]
     print(json.dumps(out))
 
 

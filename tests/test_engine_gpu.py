@@ -73,7 +73,15 @@ def test_fk_jacobian_matches_reference_golden(robot_stem, fk_variant):
     assert engine.launch_count() - launches == 3 * len(g["fk_links"])
 
 
-def test_inverse_dynamics_matches_reference_golden(robot_stem):
+@pytest.fixture(params=[1, 0], ids=["packed_f32x2", "scalar"])
+def rnea_variant(request):
+    """Both arithmetic variants of the inverse-dynamics kernel must give the same parity."""
+    engine.set_option("rnea_packed", request.param)
+    yield request.param
+    engine.set_option("rnea_packed", 1)
+
+
+def test_inverse_dynamics_matches_reference_golden(robot_stem, rnea_variant):
     g = load_golden(robot_stem)
     m = gpu_model(robot_stem)
     q, qd, qdd = cuda(g["q"]), cuda(g["qd"]), cuda(g["qdd"])
@@ -106,7 +114,7 @@ def test_fk_jacobian_matches_oracle(batch, fk_variant):
 
 
 @pytest.mark.parametrize("batch", [1, 5, 127, 128, 129, 1003])
-def test_inverse_dynamics_matches_oracle(batch):
+def test_inverse_dynamics_matches_oracle(batch, rnea_variant):
     for stem in ("panda_no_gripper", "iiwa7", "allegro_hand_description_left", "trifinger_edu", "jaco_clean",
                  "iiwa7_allegro"):
         robot = O.load_robot(urdf_path(stem), torch.float64)

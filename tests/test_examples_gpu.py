@@ -28,3 +28,15 @@ def test_kinematic_trajectory_opt():
     import run_kinematic_trajectory_opt as ex
     hist = ex.run(n_iters=150, n_targets=2048, device="cuda:0")
     assert hist[-1] < 0.05 * hist[0]
+
+
+def test_learn_forward_dynamics_iiwa():
+    import learn_forward_dynamics_iiwa as ex
+    hist = ex.run(n_epochs=4, n_data=2000, device="cuda:0")     # n_data * dt = 8 s of sine motion
+    assert len(hist) == 4 and all(h == h for h in hist) and hist[-1] < hist[0]
+
+
+def test_learn_kinematics_of_toy():
+    import learn_kinematics_of_toy as ex
+    hist = ex.run(n_epochs=600, n_data=100, device="cuda:0")
+    assert hist[-1] < 0.5 * hist[0]
