@@ -14,7 +14,7 @@ namespace drm {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-static std::atomic<int> g_options[5] = {{-1}, {-1}, {-1}, {-1}, {-1}};   // 0: fk_variant, 1: fk_tile, 2: fk_unroll, 3: fk_packed, 4: rnea_packed
+static std::atomic<int> g_options[6] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}};   // 0: fk_variant, 1: fk_tile, 2: fk_unroll, 3: fk_packed, 4: rnea_packed, 5: host_fused
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -35,12 +35,14 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 //                  access a 16-way bank conflict, touching the tile once per column wins (9.8 vs 6.3 G cfg/s).
 //   3 "fk_packed"  (DRMB200_FK_PACKED):  1 = packed FP32x2 (FFMA2) arithmetic in the rolled chain walk (default), 0 = scalar
 //   4 "rnea_packed" (DRMB200_RNEA_PACKED): 1 = packed FP32x2 arithmetic in the RNEA kernel (default), 0 = scalar
+//   5 "host_fused" (DRMB200_HOST_FUSED): drmb200_fk_jacobian_host with page-locked buffers: 1 = one launch whose TMA copies
+//                  read / write host memory directly (default), 0 = staged H2D -> kernel -> D2H pipeline
 int get_option(int which) {
     int v = g_options[which].load(std::memory_order_relaxed);
     if (v < 0) {
-        static const char* names[5] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL", "DRMB200_FK_PACKED",
-                                       "DRMB200_RNEA_PACKED"};
-        static const int defaults[5] = {1, 0, 2, 1, 1};
+        static const char* names[6] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL", "DRMB200_FK_PACKED",
+                                       "DRMB200_RNEA_PACKED", "DRMB200_HOST_FUSED"};
+        static const int defaults[6] = {1, 0, 2, 1, 1, 1};
         const char* e = getenv(names[which]);
         v = e ? atoi(e) : defaults[which];
         g_options[which].store(v, std::memory_order_relaxed);
@@ -109,6 +111,17 @@ static std::mutex g_pipe_mu;
         }                                                                                     \
     } while (0)
 
+// device alias of a page-locked host pointer (null stays null); false for pageable memory
+static bool pinned_alias(const void* host, const void** dev) {
+    *dev = nullptr;
+    if (host == nullptr) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return false;
+    *dev = a.devicePointer;
+    return true;
+}
+
 static int fk_jacobian_host_impl(const drmb200_topology_t* topo, int32_t ee_link, int32_t device,
                                  const float* table, const float* q_host, int64_t batch, float* pos_host,
                                  float* quat_host, float* jl_host, float* ja_host) {
@@ -119,6 +132,25 @@ static int fk_jacobian_host_impl(const drmb200_topology_t* topo, int32_t ee_link
     const int n = topo->n_dofs;
     std::lock_guard<std::mutex> lock(g_pipe_mu);
     CK(cudaSetDevice(device));
+    // Fused path: when every host buffer is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) it has a
+    // device alias under unified addressing, and the kernel's own TMA bulk copies read the q tiles from and write the
+    // output tiles to HOST memory directly over PCIe -- no staging buffers in HBM, no separate copy operations, the
+    // transfer overlaps the arithmetic tile by tile inside ONE launch.  Pageable buffers take the staged pipeline below.
+    if (get_option(5) != 0) {
+        const void* dq = nullptr; const void* dpos = nullptr; const void* dquat = nullptr; const void* djl = nullptr; const void* dja = nullptr;
+        if (pinned_alias(q_host, &dq) && pinned_alias(pos_host, &dpos) && pinned_alias(quat_host, &dquat) &&
+            pinned_alias(jl_host, &djl) && pinned_alias(ja_host, &dja)) {
+            static cudaStream_t zc_stream[64] = {};
+            cudaStream_t& st = zc_stream[device & 63];
+            if (st == nullptr) CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+            int rc = fk_jacobian_device(topo, ee_link, table, static_cast<const float*>(dq), batch,
+                                        static_cast<float*>(const_cast<void*>(dpos)), static_cast<float*>(const_cast<void*>(dquat)),
+                                        static_cast<float*>(const_cast<void*>(djl)), static_cast<float*>(const_cast<void*>(dja)), st);
+            if (rc != DRMB200_OK) return rc;
+            CK(cudaStreamSynchronize(st));
+            return DRMB200_OK;
+        }
+    }
     // 64 Ki configurations per chunk (14.7 MB per stage for a 7-DoF arm).  Measured on B200/PCIe Gen5:
     // with 16 Ki chunks a 64 Ki call issues 24 async copies / launches and the ~10 us host cost of each
     // dominates (185 M cfg/s); with one chunk per 64 Ki it is 214 M cfg/s.  Larger batches pipeline
@@ -177,6 +209,7 @@ int drmb200_set_option(const char* name, int value) {
     if (name != nullptr && std::string(name) == "fk_unroll") { drm::g_options[2].store(value); return DRMB200_OK; }
     if (name != nullptr && std::string(name) == "fk_packed") { drm::g_options[3].store(value); return DRMB200_OK; }
     if (name != nullptr && std::string(name) == "rnea_packed") { drm::g_options[4].store(value); return DRMB200_OK; }
+    if (name != nullptr && std::string(name) == "host_fused") { drm::g_options[5].store(value); return DRMB200_OK; }
     drm::set_error("unknown option");
     return DRMB200_EINVAL;
 }

@@ -285,13 +285,24 @@ def test_full_size_inverse_dynamics_properties():
     assert_close(tau.cpu().numpy()[rows], o_tau.numpy(), rtol=1e-5, atol=max(1e-5, 2e-6 * float(o_tau.abs().max())), what="tau")
 
 
-def test_host_buffer_entry_point_matches_device_path():
+@pytest.mark.parametrize("mode", ["fused_pinned", "staged_pinned", "pageable"])
+def test_host_buffer_entry_point_matches_device_path(mode):
+    """Page-locked buffers: one launch whose TMA copies read / write host memory directly (default) or the staged
+    H2D -> kernel -> D2H pipeline; pageable buffers always take the staged pipeline.  All bit-identical to the device path."""
     m = gpu_model("iiwa7")
     B = 150001                                               # several pipeline chunks + a ragged tail
-    q_host = (torch.rand(B, 7) * 4 - 2).pin_memory()
-    outs = [torch.empty(B, 3).pin_memory(), torch.empty(B, 4).pin_memory(), torch.empty(B, 3, 7).pin_memory(),
-            torch.empty(B, 3, 7).pin_memory()]
-    engine.fk_jacobian_host(m._topology, m._name_to_idx_map["iiwa_link_ee"], 0, m._link_table(), q_host, *outs)
+    pin = (lambda t: t.pin_memory()) if mode != "pageable" else (lambda t: t)
+    q_host = pin(torch.rand(B, 7) * 4 - 2)
+    outs = [pin(torch.zeros(B, 3)), pin(torch.zeros(B, 4)), pin(torch.zeros(B, 3, 7)), pin(torch.zeros(B, 3, 7))]
+    engine.set_option("host_fused", 0 if mode == "staged_pinned" else 1)
+    table = m._link_table()
+    try:
+        launches = engine.launch_count()
+        engine.fk_jacobian_host(m._topology, m._name_to_idx_map["iiwa_link_ee"], 0, table, q_host, *outs)
+        if mode == "fused_pinned":
+            assert engine.launch_count() - launches == 1
+    finally:
+        engine.set_option("host_fused", 1)
     want = m.compute_fk_and_jacobian(q_host.to(DEV), "iiwa_link_ee")
     for got, w in zip(outs, want):
         assert torch.equal(got, w.cpu())
