@@ -187,8 +187,10 @@ int drmb200_build_link_table_backward(const float* raw, const float* table_grad,
 /*
  * Host-buffer variant of drmb200_fk_jacobian: q and the outputs are HOST pointers (pinned memory
  * gives full PCIe bandwidth; pageable memory works).  `table` is still a device pointer (it is
- * < 8 KB and lives with the model).  The call splits the batch into chunks, overlaps
- * H2D / kernel / D2H on internal streams of `device`, and returns once all outputs are on the host.
+ * < 8 KB and lives with the model).  With page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory)
+ * the kernel is launched ONCE on their device aliases and its TMA copies read / write host memory directly over PCIe
+ * (transfer fused into the compute kernel); with pageable buffers the call splits the batch into chunks and overlaps
+ * H2D / kernel / D2H on internal streams of `device`.  Either way it returns once all outputs are on the host.
  */
 int drmb200_fk_jacobian_host(const drmb200_topology_t* topo, int32_t ee_link, int32_t device,
                              const float* table, const float* q_host, int64_t batch,
