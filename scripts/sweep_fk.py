@@ -32,7 +32,7 @@ def main():
                torch.empty(big, 3, 7, device=DEV))
     stream = torch.cuda.Stream(device=DEV)
     rows = []
-    combos = [(1, 0, 1), (1, 0, 0), (1, 1, 0), (0, 0, 1)]      # (staging, unrolled, packed FP32x2)
+    combos = [(1, 0, 1), (1, 0, 0), (1, 1, 1), (0, 0, 1)]      # (staging, unrolled, packed FP32x2); unrolled is always packed
     for (variant, unroll, packed), tile in itertools.product(combos, (64, 128, 256)):
         engine.set_option("fk_variant", variant)
         engine.set_option("fk_unroll", unroll)
