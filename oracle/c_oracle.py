@@ -72,3 +72,13 @@ class CRobot:
         fn(ctypes.byref(self.struct), self._p(q), self._p(qd), self._p(qdd), ctypes.c_long(B), ctypes.c_int(gravity),
            ctypes.c_int(damping), self._p(tau), ctypes.c_int(n_threads))
         return tau
+
+    def forward_dynamics(self, q, qd, f, gravity=True, damping=False, n_threads=0):
+        q, qd, f = (np.ascontiguousarray(t, dtype=self.dtype) for t in (q, qd, f))
+        B, n = q.shape
+        qdd = np.zeros((B, n), self.dtype)
+        fn = getattr(_load(), f"drm_oracle_forward_dynamics_{self.suffix}")
+        fn.restype = None
+        fn(ctypes.byref(self.struct), self._p(q), self._p(qd), self._p(f), ctypes.c_long(B), ctypes.c_int(gravity),
+           ctypes.c_int(damping), self._p(qdd), ctypes.c_int(n_threads))
+        return qdd

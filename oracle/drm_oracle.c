@@ -1,4 +1,4 @@
-/* TEST INFRASTRUCTURE -- plain C restatement of the reference's FK / Jacobian / RNEA algorithm.
+/* TEST INFRASTRUCTURE -- plain C restatement of the reference's FK / Jacobian / RNEA / articulated-body algorithms.
  *
  * A second, independent CPU oracle (the first is oracle/drm_oracle.py): scalar code, one joint
  * configuration at a time, pthreads over the batch, compiled twice (float and double) from this file
@@ -16,6 +16,7 @@
  *   quaternion           spatial_vector_algebra.py:108-136
  *   jacobian             robot_model.py:627-667
  *   rnea                 robot_model.py:251-375, spatial_vector_algebra.py:204-224, 281-291, 321-338
+ *   forward dynamics     robot_model.py:488-624 (6x6 articulated inertias), spatial_vector_algebra.py:138-154, 340-372
  */
 #include <math.h>
 #include <pthread.h>
@@ -258,4 +259,120 @@ void FN(drm_oracle_inverse_dynamics)(const FN(drm_oracle_robot)* rb, const REAL*
                                      long batch, int gravity, int damping, REAL* tau, int n_threads) {
     FN(id_ctx) ctx = {rb, q, qd, qdd, gravity, damping, tau};
     FN(parallel_rows)(FN(id_row), &ctx, batch, n_threads);
+}
+
+/* ---- articulated-body forward dynamics (robot_model.py:488-624), 6x6 matrices / 6-vectors in [ang; lin] order ---- */
+static void mat6_vec(const REAL* A, const REAL* x, REAL* y) {
+    for (int i = 0; i < 6; ++i) { REAL s = 0; for (int j = 0; j < 6; ++j) s += A[6 * i + j] * x[j]; y[i] = s; }
+}
+/* X = CoordinateTransform.to_matrix() of the joint pose (sva:138-154): [[R^T, 0], [-R^T t^, R^T]] */
+static void motion_matrix(const REAL* Rj, const REAL* t, REAL* X) {
+    const REAL S[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+    REAL Rt[9], RtS[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Rt[3 * r + c] = Rj[3 * c + r];
+    mat_mul(Rt, S, RtS);
+    memset(X, 0, 36 * sizeof(REAL));
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) {
+        X[6 * r + c] = Rt[3 * r + c];
+        X[6 * (r + 3) + c] = -RtS[3 * r + c];
+        X[6 * (r + 3) + c + 3] = Rt[3 * r + c];
+    }
+}
+/* get_spatial_mat (sva:340-372): [[Io, mc^], [(mc^)^T, m 1]], Io = I_c + m S(c) S(c)^T, NOT symmetrised */
+static void spatial_inertia(const FN(drm_oracle_robot)* rb, int i, REAL* I6) {
+    const REAL m = rb->mass[i];
+    const REAL* c = rb->com + 3 * i;
+    const REAL S[9] = {0, -c[2], c[1], c[2], 0, -c[0], -c[1], c[0], 0};
+    REAL St[9], SSt[9];
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) St[3 * r + k] = S[3 * k + r];
+    mat_mul(S, St, SSt);
+    memset(I6, 0, 36 * sizeof(REAL));
+    for (int r = 0; r < 3; ++r) for (int k = 0; k < 3; ++k) {
+        I6[6 * r + k] = rb->inertia[9 * i + 3 * r + k] + m * SSt[3 * r + k];
+        I6[6 * r + k + 3] = m * S[3 * r + k];
+        I6[6 * (r + 3) + k] = m * S[3 * k + r];
+    }
+    I6[21] = I6[28] = I6[35] = m;
+}
+
+typedef struct { const FN(drm_oracle_robot)* rb; const REAL *q, *qd, *f; int gravity, damping; REAL* qdd; } FN(fd_ctx);
+static void FN(fd_row)(void* vctx, long b) {
+    const FN(fd_ctx)* x = (const FN(fd_ctx)*)vctx;
+    const FN(drm_oracle_robot)* rb = x->rb;
+    const int N = rb->n_links, n = rb->n_dofs;
+    const REAL* qb = x->q + b * n;
+    const REAL* qdb = x->qd + b * n;
+    const REAL* fb = x->f + b * n;
+    REAL* out = x->qdd + b * n;
+    static __thread REAL IA[MAXL][36], X[MAXL][36];
+    REAL Rj[MAXL][9], w[MAXL][3], v[MAXL][3], c[MAXL][6], pA[MAXL][6], U[MAXL][6], d[MAXL], u[MAXL], S[MAXL][6], acc[MAXL][6];
+    memset(w[0], 0, sizeof(w[0])); memset(v[0], 0, sizeof(v[0]));
+    for (int i = 1; i < N; ++i) {                                   /* kinematic state + bias terms (:524-545) */
+        const int par = rb->parent[i];
+        const REAL* r = rb->trans + 3 * i;
+        REAL jw[3] = {0, 0, 0}, t[3], s[3], hl[3], ha[3];
+        joint_rot(rb, i, qb, Rj[i]);
+        motion_matrix(Rj[i], r, X[i]);
+        for (int k = 0; k < 3; ++k) S[i][k] = rb->axis[3 * i + k], S[i][k + 3] = 0;       /* zero for fixed links (:550-553) */
+        if (rb->dof[i] >= 0) for (int k = 0; k < 3; ++k) jw[k] = qdb[rb->dof[i]] * rb->axis[3 * i + k];
+        matT_vec(Rj[i], w[par], w[i]);
+        cross3(w[par], r, t);
+        for (int k = 0; k < 3; ++k) s[k] = v[par][k] + t[k];
+        matT_vec(Rj[i], s, v[i]);
+        for (int k = 0; k < 3; ++k) w[i][k] += jw[k];
+        cross3(w[i], jw, c[i]);                                     /* cross_motion_vec, joint_vel.lin = 0 (:541) */
+        cross3(v[i], jw, c[i] + 3);
+        inertia_times(rb, i, w[i], v[i], hl, ha);
+        cross3(w[i], ha, t); cross3(v[i], hl, s);                   /* cross_force_vec (:543) */
+        for (int k = 0; k < 3; ++k) pA[i][k] = t[k] + s[k];
+        cross3(w[i], hl, pA[i] + 3);
+        spatial_inertia(rb, i, IA[i]);
+    }
+    for (int i = N - 1; i >= 1; --i) {                              /* articulated inertias (:547-596) */
+        const int par = rb->parent[i];
+        mat6_vec(IA[i], S[i], U[i]);
+        d[i] = 0; u[i] = 0;
+        for (int k = 0; k < 6; ++k) { d[i] += S[i][k] * U[i][k]; u[i] -= pA[i][k] * S[i][k]; }
+        if (rb->dof[i] >= 0) {
+            REAL fk = fb[rb->dof[i]];
+            if (x->damping) fk -= rb->damping[i] * qdb[rb->dof[i]];
+            u[i] += fk;
+        }
+        if (par > 0) {
+            REAL IAp[36], T1[36], tmp[6], pa[6];
+            const REAL dd = d[i] + (REAL)1e-37;
+            for (int r = 0; r < 6; ++r) for (int k = 0; k < 6; ++k) IAp[6 * r + k] = IA[i][6 * r + k] - U[i][r] * (U[i][k] / dd);
+            mat6_vec(IAp, c[i], tmp);
+            for (int k = 0; k < 6; ++k) pa[k] = pA[i][k] + tmp[k] + U[i][k] * (u[i] / dd);
+            for (int r = 0; r < 6; ++r) for (int k = 0; k < 6; ++k) {        /* X^T IA' */
+                REAL s = 0; for (int m = 0; m < 6; ++m) s += X[i][6 * m + r] * IAp[6 * m + k]; T1[6 * r + k] = s;
+            }
+            for (int r = 0; r < 6; ++r) for (int k = 0; k < 6; ++k) {        /* (X^T IA') X */
+                REAL s = 0; for (int m = 0; m < 6; ++m) s += T1[6 * r + m] * X[i][6 * m + k]; IA[par][6 * r + k] += s;
+            }
+            REAL nl[3], na[3], t[3];                                /* SpatialForceVec.transform (sva:281-291) */
+            mat_vec(Rj[i], pa + 3, nl);
+            mat_vec(Rj[i], pa, na);
+            cross3(rb->trans + 3 * i, nl, t);
+            for (int k = 0; k < 3; ++k) { pA[par][k] += t[k] + na[k]; pA[par][k + 3] += nl[k]; }
+        }
+    }
+    memset(acc[0], 0, sizeof(acc[0]));
+    acc[0][5] = x->gravity ? (REAL)9.81 : 0;
+    for (int i = 1; i < N; ++i) {                                   /* accelerations (:604-622) */
+        mat6_vec(X[i], acc[rb->parent[i]], acc[i]);
+        for (int k = 0; k < 6; ++k) acc[i][k] += c[i][k];
+        if (rb->dof[i] >= 0) {
+            REAL s = 0;
+            for (int k = 0; k < 6; ++k) s += U[i][k] * acc[i][k];
+            const REAL qdd = ((REAL)1 / d[i]) * (u[i] - s);
+            out[rb->dof[i]] = qdd;
+            for (int k = 0; k < 6; ++k) acc[i][k] += S[i][k] * qdd;
+        }
+    }
+}
+void FN(drm_oracle_forward_dynamics)(const FN(drm_oracle_robot)* rb, const REAL* q, const REAL* qd, const REAL* f,
+                                     long batch, int gravity, int damping, REAL* qdd, int n_threads) {
+    FN(fd_ctx) ctx = {rb, q, qd, f, gravity, damping, qdd};
+    FN(parallel_rows)(FN(fd_row), &ctx, batch, n_threads);
 }

@@ -139,6 +139,15 @@ def bench_forward_dynamics(stem_cls, batch):
                 best, res["cpu_port_threads"] = rate, threads
         res["cpu_port_configs_per_s"] = best
         res["cpu_port_sample"] = f"{rows} rows x 3 calls, torch CPU port of robot_model.py:488-624"
+        # and the scalar C restatement on all host cores (oracle/drm_oracle.c, pthreads over the batch)
+        from oracle.c_oracle import CRobot
+        cr = CRobot(robot)
+        nq, nqd, nf = (t.cpu().numpy() for t in (sets[0][0], sets[0][1], fs[0]))
+        cr.forward_dynamics(nq[:4096], nqd[:4096], nf[:4096], True, True)
+        t0 = time.perf_counter()
+        cr.forward_dynamics(nq, nqd, nf, True, True)
+        res["cpu_c_port_configs_per_s"] = batch / (time.perf_counter() - t0)
+        res["cpu_c_port_cores"] = os.cpu_count()
     return res
 
 

@@ -61,3 +61,31 @@ def test_per_element_quaternion_loop_matches_vectorised_and_reference_golden():
     Rrand = torch.linalg.qr(torch.randn(257, 3, 3, generator=torch.Generator().manual_seed(0)))[0]
     Rrand = Rrand * torch.sign(torch.linalg.det(Rrand))[:, None, None]            # proper rotations, all four branches
     assert_close(O.quaternion_per_element(Rrand).numpy(), O.quaternion(Rrand).numpy(), rtol=1e-5, atol=1e-6, what="random R")
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float32, 2e-4), (np.float64, 2e-4)])
+def test_c_forward_dynamics_matches_reference_golden(robot_stem, dtype, tol):
+    """C restatement of the articulated-body algorithm vs the reference's own fp32 outputs (tests/golden/*.fd.npz),
+    per configuration relative to its largest acceleration (the hand models divide by inertias ~1e-7)."""
+    import os
+    from conftest import GOLDEN_DIR
+    g = np.load(os.path.join(GOLDEN_DIR, robot_stem + ".fd.npz"))
+    robot = O.load_robot(urdf_path(robot_stem), torch.float64)
+    cr = CRobot(robot, dtype)
+    for grav in (0, 1):
+        for damp in (0, 1):
+            got = cr.forward_dynamics(g["q"], g["qd"], g["f"], bool(grav), bool(damp), n_threads=2)
+            want = g[f"qdd.g{grav}d{damp}"]
+            assert np.all(np.abs(got - want) <= tol * np.abs(want).max(axis=1, keepdims=True) + 1e-6), (grav, damp)
+
+
+def test_c_forward_dynamics_matches_torch_oracle_nonsymmetric():
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float64)
+    gen = torch.Generator().manual_seed(5)
+    robot.inertia = robot.inertia + 0.05 * robot.inertia.abs().amax(dim=(1, 2), keepdim=True) * torch.randn(
+        robot.inertia.shape, generator=gen, dtype=torch.float64)
+    q, qd, _ = O.sample_inputs(robot, 64, seed=8, dtype=torch.float64)
+    f = torch.randn(64, 7, generator=gen, dtype=torch.float64)
+    want = O.forward_dynamics(robot, q, qd, f, True, True).numpy()
+    got = CRobot(robot, np.float64).forward_dynamics(q.numpy(), qd.numpy(), f.numpy(), True, True)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-9 * np.abs(want).max())
