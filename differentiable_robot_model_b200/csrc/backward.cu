@@ -52,7 +52,7 @@ struct FkBwdSmem {
         gja = o; o += tile * 3 * n;
         table = o; o += len * 12;
         link = o; o += len * 2 * tile;                   // per path link: cos, sin -- slot-major (R~, p are re-derived)
-        scratch = o; o += 12 * (tile + 1);
+        scratch = o; o += block_accumulate_floats(12, tile);
         acc = o; o += len * 12;                          // canonical (F~, r~) gradient per path link
         total_floats = o;
     }

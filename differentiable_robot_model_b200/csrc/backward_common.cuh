@@ -11,24 +11,40 @@ constexpr float GRAVITY_B = 9.81f;
 // ---------------------------------------------------------------------------------------------
 // block-level sum of NV per-thread values into the CTA accumulator row `acc_row` (entries map(j))
 // ---------------------------------------------------------------------------------------------
+// Transposed, two stages, fixed order (deterministic): every thread drops its NV <= 32 values into a padded scratch
+// matrix; in each warp lane j adds up value j of the warp's 32 threads (32 independent conflict-free loads, four
+// interleaved add chains -- no serial shuffle trees, whose latency these low-occupancy kernels cannot hide); warp 0
+// then adds the per-warp partials.  Scratch: block_accumulate_floats(NV, T) floats.
+__host__ __device__ constexpr int block_accumulate_floats(int nv, int t) { return nv * (t + 1) + (t / 32) * 32; }
+
 template <int NV, int T, typename Map>
 __device__ __forceinline__ void block_accumulate(float* scratch, float* acc_row, const float (&vals)[NV], bool active,
                                                  Map map) {
+    static_assert(NV <= 32 && T % 32 == 0, "one lane per value");
     constexpr int SCR_LD = T + 1;             // padded leading dimension of the reduction scratch
+    constexpr int NW = T / 32;
+    float* partial = scratch + NV * SCR_LD;   // [NW][32]
     const int tid = threadIdx.x;
 #pragma unroll
     for (int j = 0; j < NV; ++j) scratch[j * SCR_LD + tid] = active ? vals[j] : 0.f;
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
-    for (int j = warp; j < NV; j += T / 32) {
-        float x = 0.f;
+    if (lane < NV) {
+        const float* row = scratch + lane * SCR_LD + warp * 32;
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < T / 32; ++c) x += scratch[j * SCR_LD + lane + 32 * c];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0) acc_row[map(j)] += x;
+        for (int c = 0; c < 32; c += 4) { s0 += row[c]; s1 += row[c + 1]; s2 += row[c + 2]; s3 += row[c + 3]; }
+        const float s = (s0 + s1) + (s2 + s3);
+        if (NW == 1) acc_row[map(lane)] += s;
+        else partial[warp * 32 + lane] = s;
     }
     __syncthreads();
+    if (NW > 1 && warp == 0 && lane < NV) {
+        float s = partial[lane];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) s += partial[w * 32 + lane];
+        acc_row[map(lane)] += s;
+    }
 }
 
 __device__ __forceinline__ void tile_load_or_zero(float* dst, const float* src, int nfloats, int total, bool vec_ok) {

@@ -54,7 +54,7 @@ struct RneaBwdSmem {
         link = o; o += n_links * LSTATE * tile;
         slots = o; o += n_slots * 12 * tile;      // forward: branch-point motion states; backward: adjoint accumulators
         tips = o; o += n_tips * 12 * tile;        // motion state of every chain end
-        scratch = o; o += 25 * (tile + 1);
+        scratch = o; o += block_accumulate_floats(25, tile);
         acc = o; o += n_links * DRMB200_TABLE_STRIDE;
         total_floats = o;
     }
@@ -364,7 +364,7 @@ struct RneaInertialSmem {
         g = o; o += tile * n;
         table = o; o += n_links * DRMB200_TABLE_STRIDE;
         slots = o; o += n_slots * 18 * tile;
-        scratch = o; o += 14 * (tile + 1);
+        scratch = o; o += block_accumulate_floats(14, tile);
         acc = o; o += n_links * DRMB200_TABLE_STRIDE;
         total_floats = o;
     }
