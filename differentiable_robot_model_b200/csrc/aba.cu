@@ -109,6 +109,78 @@ __device__ __forceinline__ void sub_outer(M3& m, V3 x, V3 y) {      // m -= x y^
 }
 __device__ __forceinline__ M3 conj_by(const M3& M, const M3& Y) { return mulNT(mul(M, Y), M); }   // M Y M^T
 
+// ---- element-wise PAIR of two 3x3 blocks (lo | hi) in packed FP32x2 registers -------------------------------------
+struct M3PP { f32x2 a00, a01, a02, a10, a11, a12, a20, a21, a22; };
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ float hsum2(f32x2 v) { float lo, hi; upk2(v, lo, hi); return lo + hi; }
+__device__ __forceinline__ M3PP pkm(const M3& lo, const M3& hi) {
+    M3PP r;
+    r.a00 = pk2(lo.a00, hi.a00); r.a01 = pk2(lo.a01, hi.a01); r.a02 = pk2(lo.a02, hi.a02);
+    r.a10 = pk2(lo.a10, hi.a10); r.a11 = pk2(lo.a11, hi.a11); r.a12 = pk2(lo.a12, hi.a12);
+    r.a20 = pk2(lo.a20, hi.a20); r.a21 = pk2(lo.a21, hi.a21); r.a22 = pk2(lo.a22, hi.a22);
+    return r;
+}
+__device__ __forceinline__ void upkm(const M3PP& p, M3& lo, M3& hi) {
+    upk2(p.a00, lo.a00, hi.a00); upk2(p.a01, lo.a01, hi.a01); upk2(p.a02, lo.a02, hi.a02);
+    upk2(p.a10, lo.a10, hi.a10); upk2(p.a11, lo.a11, hi.a11); upk2(p.a12, lo.a12, hi.a12);
+    upk2(p.a20, lo.a20, hi.a20); upk2(p.a21, lo.a21, hi.a21); upk2(p.a22, lo.a22, hi.a22);
+}
+__device__ __forceinline__ M3PP zero_pp() { const M3 z = zero3(); return pkm(z, z); }
+__device__ __forceinline__ M3PP add_pp(const M3PP& a, const M3PP& b) {
+    M3PP r;
+    r.a00 = add2(a.a00, b.a00); r.a01 = add2(a.a01, b.a01); r.a02 = add2(a.a02, b.a02);
+    r.a10 = add2(a.a10, b.a10); r.a11 = add2(a.a11, b.a11); r.a12 = add2(a.a12, b.a12);
+    r.a20 = add2(a.a20, b.a20); r.a21 = add2(a.a21, b.a21); r.a22 = add2(a.a22, b.a22);
+    return r;
+}
+// (M Y_lo | M Y_hi): scalar matrix from the left, same association order as mul(M3, M3)
+__device__ __forceinline__ M3PP mul_left_pp(const M3& m, const M3PP& y) {
+    M3PP r;
+    r.a00 = fma2(bc2(m.a00), y.a00, fma2(bc2(m.a01), y.a10, mul2(bc2(m.a02), y.a20)));
+    r.a01 = fma2(bc2(m.a00), y.a01, fma2(bc2(m.a01), y.a11, mul2(bc2(m.a02), y.a21)));
+    r.a02 = fma2(bc2(m.a00), y.a02, fma2(bc2(m.a01), y.a12, mul2(bc2(m.a02), y.a22)));
+    r.a10 = fma2(bc2(m.a10), y.a00, fma2(bc2(m.a11), y.a10, mul2(bc2(m.a12), y.a20)));
+    r.a11 = fma2(bc2(m.a10), y.a01, fma2(bc2(m.a11), y.a11, mul2(bc2(m.a12), y.a21)));
+    r.a12 = fma2(bc2(m.a10), y.a02, fma2(bc2(m.a11), y.a12, mul2(bc2(m.a12), y.a22)));
+    r.a20 = fma2(bc2(m.a20), y.a00, fma2(bc2(m.a21), y.a10, mul2(bc2(m.a22), y.a20)));
+    r.a21 = fma2(bc2(m.a20), y.a01, fma2(bc2(m.a21), y.a11, mul2(bc2(m.a22), y.a21)));
+    r.a22 = fma2(bc2(m.a20), y.a02, fma2(bc2(m.a21), y.a12, mul2(bc2(m.a22), y.a22)));
+    return r;
+}
+// (Y_lo M^T | Y_hi M^T)
+__device__ __forceinline__ M3PP mul_rightT_pp(const M3PP& y, const M3& m) {
+    M3PP r;
+    r.a00 = fma2(y.a00, bc2(m.a00), fma2(y.a01, bc2(m.a01), mul2(y.a02, bc2(m.a02))));
+    r.a01 = fma2(y.a00, bc2(m.a10), fma2(y.a01, bc2(m.a11), mul2(y.a02, bc2(m.a12))));
+    r.a02 = fma2(y.a00, bc2(m.a20), fma2(y.a01, bc2(m.a21), mul2(y.a02, bc2(m.a22))));
+    r.a10 = fma2(y.a10, bc2(m.a00), fma2(y.a11, bc2(m.a01), mul2(y.a12, bc2(m.a02))));
+    r.a11 = fma2(y.a10, bc2(m.a10), fma2(y.a11, bc2(m.a11), mul2(y.a12, bc2(m.a12))));
+    r.a12 = fma2(y.a10, bc2(m.a20), fma2(y.a11, bc2(m.a21), mul2(y.a12, bc2(m.a22))));
+    r.a20 = fma2(y.a20, bc2(m.a00), fma2(y.a21, bc2(m.a01), mul2(y.a22, bc2(m.a02))));
+    r.a21 = fma2(y.a20, bc2(m.a10), fma2(y.a21, bc2(m.a11), mul2(y.a22, bc2(m.a12))));
+    r.a22 = fma2(y.a20, bc2(m.a20), fma2(y.a21, bc2(m.a21), mul2(y.a22, bc2(m.a22))));
+    return r;
+}
+__device__ __forceinline__ M3PP conj_pp(const M3& m, const M3PP& y) { return mul_rightT_pp(mul_left_pp(m, y), m); }   // M Y M^T
+// skew(r) Y on both lanes: column j of the result = r x column j
+__device__ __forceinline__ M3PP left_cross_pp(V3 r, const M3PP& y) {
+    M3PP o;
+    o.a00 = fma2(bc2(r.y), y.a20, mul2(bc2(-r.z), y.a10)); o.a10 = fma2(bc2(r.z), y.a00, mul2(bc2(-r.x), y.a20)); o.a20 = fma2(bc2(r.x), y.a10, mul2(bc2(-r.y), y.a00));
+    o.a01 = fma2(bc2(r.y), y.a21, mul2(bc2(-r.z), y.a11)); o.a11 = fma2(bc2(r.z), y.a01, mul2(bc2(-r.x), y.a21)); o.a21 = fma2(bc2(r.x), y.a11, mul2(bc2(-r.y), y.a01));
+    o.a02 = fma2(bc2(r.y), y.a22, mul2(bc2(-r.z), y.a12)); o.a12 = fma2(bc2(r.z), y.a02, mul2(bc2(-r.x), y.a22)); o.a22 = fma2(bc2(r.x), y.a12, mul2(bc2(-r.y), y.a02));
+    return o;
+}
+// Y -= x yp^T with a scalar left vector x and a PAIR right vector yp (one vector per lane)
+__device__ __forceinline__ void sub_outer_pp(M3PP& m, V3 x, const V3P& yp) {
+    m.a00 = fma2(bc2(-x.x), yp.x, m.a00); m.a01 = fma2(bc2(-x.x), yp.y, m.a01); m.a02 = fma2(bc2(-x.x), yp.z, m.a02);
+    m.a10 = fma2(bc2(-x.y), yp.x, m.a10); m.a11 = fma2(bc2(-x.y), yp.y, m.a11); m.a12 = fma2(bc2(-x.y), yp.z, m.a12);
+    m.a20 = fma2(bc2(-x.z), yp.x, m.a20); m.a21 = fma2(bc2(-x.z), yp.y, m.a21); m.a22 = fma2(bc2(-x.z), yp.z, m.a22);
+}
+
 template <int T>
 __global__ void __launch_bounds__(T)
 aba_kernel(const __grid_constant__ TreeProgram prog, const AbaArgs args) {
@@ -196,35 +268,37 @@ aba_kernel(const __grid_constant__ TreeProgram prog, const AbaArgs args) {
         }
 
         // ---- pass 2: leaves -> root, articulated inertias (robot_model.py:547-596) ---------------------------
+        // Packed FP32x2: the 6x6 travels as two element-wise PAIRS of 3x3 blocks, AB = (A | B) and CD = (C | D) -- both
+        // blocks of a pair see the same rotation M . M^T, the same left cross product with r and the same left factor of
+        // the rank-1 update, so those cost one FFMA2 per two scalar FMAs.
         {
-            M6 cI;                       // contribution of link i+1 to its parent i, through registers
+            M3PP cAB = zero_pp(), cCD = zero_pp();       // contribution of link i+1 to its parent i, through registers
             V3 c_pang = zero, c_plin = zero;
-            cI.A = cI.B = cI.C = cI.D = zero3();
             for (int i = N - 1; i >= 1; --i) {
                 const LinkRow C = load_row(s_tab + i * DRMB200_TABLE_STRIDE);
                 float* lk = lk0 + i * ABA_LINK * T;
-                M6 IA;
-                IA.A = C.Io;                                                       // sva:340-372
-                IA.B = skew(C.mc);
-                IA.C = transpose(IA.B);
-                IA.D = zero3(); IA.D.a00 = IA.D.a11 = IA.D.a22 = C.m;
+                M3 D0 = zero3(); D0.a00 = D0.a11 = D0.a22 = C.m;
+                const M3 B0 = skew(C.mc);
+                M3PP AB = pkm(C.Io, B0), CD = pkm(transpose(B0), D0);               // sva:340-372
                 V3 p_ang = ldv(lk + 6 * T, T), p_lin = ldv(lk + 9 * T, T);
                 if (i + 1 < N && prog.psrc[i + 1] == 0) {
-                    IA.A = IA.A + cI.A; IA.B = IA.B + cI.B; IA.C = IA.C + cI.C; IA.D = IA.D + cI.D;
+                    AB = add_pp(AB, cAB); CD = add_pp(CD, cCD);
                     p_ang = p_ang + c_pang; p_lin = p_lin + c_plin;
                 }
                 const int sv = prog.save[i];
                 if (sv >= 0) {
                     const float* sl = sl0 + sv * ABA_SLOT * T;
-                    IA.A = IA.A + ldm(sl, T); IA.B = IA.B + ldm(sl + 9 * T, T);
-                    IA.C = IA.C + ldm(sl + 18 * T, T); IA.D = IA.D + ldm(sl + 27 * T, T);
+                    AB = add_pp(AB, pkm(ldm(sl, T), ldm(sl + 9 * T, T)));
+                    CD = add_pp(CD, pkm(ldm(sl + 18 * T, T), ldm(sl + 27 * T, T)));
                     p_ang = p_ang + ldv(sl + 36 * T, T); p_lin = p_lin + ldv(sl + 39 * T, T);
                 }
                 const int c = prog.dof[i];
                 V3 Ua = zero, Ul = zero;
                 float d = 0.f, u = 0.f;
                 if (c >= 0) {
-                    Ua = col2(IA.A); Ul = col2(IA.C);                              // U = IA S, S = e_z(ang)   (:555)
+                    float t;
+                    upk2(AB.a02, Ua.x, t); upk2(AB.a12, Ua.y, t); upk2(AB.a22, Ua.z, t);    // U = IA S, S = e_z(ang)   (:555)
+                    upk2(CD.a02, Ul.x, t); upk2(CD.a12, Ul.y, t); upk2(CD.a22, Ul.z, t);
                     d = Ua.z;                                                      // S . U                    (:557)
                     float fk = frow[c];
                     if (damp) fk = fmaf(-C.d, qdrow[c], fk);                       // f -= damping * qd        (:516-521)
@@ -236,41 +310,48 @@ aba_kernel(const __grid_constant__ TreeProgram prog, const AbaArgs args) {
                     V3 pa_ang = p_ang, pa_lin = p_lin;
                     if (c >= 0) {
                         const float inv = 1.f / (d + ABA_EPS);                     // (:569-571, :581-583)
-                        const V3 Uda = inv * Ua, Udl = inv * Ul;
-                        sub_outer(IA.A, Ua, Uda); sub_outer(IA.B, Ua, Udl);        // IA - U Ud^T              (:575-577)
-                        sub_outer(IA.C, Ul, Uda); sub_outer(IA.D, Ul, Udl);
-                        const float cax = lk[2 * T], cay = lk[3 * T], clx = lk[4 * T], cly = lk[5 * T];
+                        const V3P Ud = pk3(inv * Ua, inv * Ul);                    // (Ud_ang | Ud_lin)
+                        sub_outer_pp(AB, Ua, Ud);                                  // IA - U Ud^T              (:575-577)
+                        sub_outer_pp(CD, Ul, Ud);
+                        const f32x2 cx = pk2(lk[2 * T], lk[4 * T]), cy = pk2(lk[3 * T], lk[5 * T]);   // (c_ang | c_lin), z = 0
                         const float ud = u * inv;
                         // pa = pA + IA' c + U ud                                                               (:579-585)
-                        pa_ang.x += fmaf(IA.A.a00, cax, fmaf(IA.A.a01, cay, fmaf(IA.B.a00, clx, fmaf(IA.B.a01, cly, Ua.x * ud))));
-                        pa_ang.y += fmaf(IA.A.a10, cax, fmaf(IA.A.a11, cay, fmaf(IA.B.a10, clx, fmaf(IA.B.a11, cly, Ua.y * ud))));
-                        pa_ang.z += fmaf(IA.A.a20, cax, fmaf(IA.A.a21, cay, fmaf(IA.B.a20, clx, fmaf(IA.B.a21, cly, Ua.z * ud))));
-                        pa_lin.x += fmaf(IA.C.a00, cax, fmaf(IA.C.a01, cay, fmaf(IA.D.a00, clx, fmaf(IA.D.a01, cly, Ul.x * ud))));
-                        pa_lin.y += fmaf(IA.C.a10, cax, fmaf(IA.C.a11, cay, fmaf(IA.D.a10, clx, fmaf(IA.D.a11, cly, Ul.y * ud))));
-                        pa_lin.z += fmaf(IA.C.a20, cax, fmaf(IA.C.a21, cay, fmaf(IA.D.a20, clx, fmaf(IA.D.a21, cly, Ul.z * ud))));
+                        pa_ang.x += hsum2(fma2(AB.a00, cx, mul2(AB.a01, cy))) + Ua.x * ud;
+                        pa_ang.y += hsum2(fma2(AB.a10, cx, mul2(AB.a11, cy))) + Ua.y * ud;
+                        pa_ang.z += hsum2(fma2(AB.a20, cx, mul2(AB.a21, cy))) + Ua.z * ud;
+                        pa_lin.x += hsum2(fma2(CD.a00, cx, mul2(CD.a01, cy))) + Ul.x * ud;
+                        pa_lin.y += hsum2(fma2(CD.a10, cx, mul2(CD.a11, cy))) + Ul.y * ud;
+                        pa_lin.z += hsum2(fma2(CD.a20, cx, mul2(CD.a21, cy))) + Ul.z * ud;
                     }
                     // X^T IA' X = T^T (M IA' M^T) T with T = [[1, 0], [-r^, 1]]                                 (:587-595)
                     M3 M = C.F;
                     if (c >= 0) rotate_z(M, cs, sn);
-                    M6 Y;
-                    Y.D = conj_by(M, IA.D);
-                    Y.B = conj_by(M, IA.B) + left_cross(C.r, Y.D);
-                    Y.C = conj_by(M, IA.C) - right_cross(Y.D, C.r);
-                    Y.A = conj_by(M, IA.A) + left_cross(C.r, Y.C) - right_cross(conj_by(M, IA.B), C.r);
+                    M3PP Yab = conj_pp(M, AB);                                     // (A^ | B^)
+                    M3PP Ycd = conj_pp(M, CD);                                     // (C^ | D^)
+                    Yab = add_pp(Yab, left_cross_pp(C.r, Ycd));                    // (A^ + r^ C^ | B^ + r^ D^) = (. | Y_B)
+                    {
+                        M3 Ya, Yb, Yc, Yd;
+                        upkm(Yab, Ya, Yb); upkm(Ycd, Yc, Yd);
+                        Ya = Ya - right_cross(Yb, C.r);                            // Y_A = A^ + r^ C^ - Y_B r^
+                        Yc = Yc - right_cross(Yd, C.r);                            // Y_C = C^ - D^ r^
+                        Yab = pkm(Ya, Yb); Ycd = pkm(Yc, Yd);
+                    }
                     // force transform (sva:281-291)
                     const V3 q_lin = mul(M, pa_lin);
                     const V3 q_ang = cross_add(C.r, q_lin, mul(M, pa_ang));
-                    if (P == i - 1) { cI = Y; c_pang = q_ang; c_plin = q_lin; }
+                    if (P == i - 1) { cAB = Yab; cCD = Ycd; c_pang = q_ang; c_plin = q_lin; }
                     else {
                         float* sl = sl0 + (int)prog.save[P] * ABA_SLOT * T;
+                        M3 Ya, Yb, Yc, Yd;
+                        upkm(Yab, Ya, Yb); upkm(Ycd, Yc, Yd);
                         if (prog.accw[i] != 2) {
-                            Y.A = Y.A + ldm(sl, T); Y.B = Y.B + ldm(sl + 9 * T, T);
-                            Y.C = Y.C + ldm(sl + 18 * T, T); Y.D = Y.D + ldm(sl + 27 * T, T);
+                            Ya = Ya + ldm(sl, T); Yb = Yb + ldm(sl + 9 * T, T);
+                            Yc = Yc + ldm(sl + 18 * T, T); Yd = Yd + ldm(sl + 27 * T, T);
                             stv(sl + 36 * T, T, ldv(sl + 36 * T, T) + q_ang); stv(sl + 39 * T, T, ldv(sl + 39 * T, T) + q_lin);
                         } else {
                             stv(sl + 36 * T, T, q_ang); stv(sl + 39 * T, T, q_lin);
                         }
-                        stm(sl, T, Y.A); stm(sl + 9 * T, T, Y.B); stm(sl + 18 * T, T, Y.C); stm(sl + 27 * T, T, Y.D);
+                        stm(sl, T, Ya); stm(sl + 9 * T, T, Yb); stm(sl + 18 * T, T, Yc); stm(sl + 27 * T, T, Yd);
                     }
                 }
                 stv(lk + 6 * T, T, Ua); stv(lk + 9 * T, T, Ul);                    // pA_i is dead: keep U, u, d for pass 3

@@ -151,6 +151,29 @@ def bench_forward_dynamics(stem_cls, batch):
     return res
 
 
+def bench_kinematic_state(stem_cls, batch):
+    """All-links pose (+ quaternion) (+ velocity) kernel and the pose-only FK of one link."""
+    m = stem_cls(device=DEV)
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    n, N = robot.n_dofs, len(robot.names)
+    q, qd, _ = (t.to(DEV) for t in O.sample_inputs(robot, batch, seed=0))
+    table, topo = m._link_table(), m._topology
+    res = {"batch": batch, "n_links": N}
+    for name, kw, by in (("poses", dict(qd=None, want_poses=True, want_quats=False), 4 * n + 48 * N),
+                         ("poses_quats", dict(qd=None, want_poses=True, want_quats=True), 4 * n + 64 * N),
+                         ("poses_vels", dict(qd=qd, want_poses=True, want_quats=False), 8 * n + 72 * N)):
+        ms = timed(lambda i: engine.kinematic_state_raw(topo, table, q, **kw), 20)
+        res[name] = {"ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
+                     "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK}
+    ee = m._name_to_idx_map[robot.names[-1]]
+    out = (torch.empty(batch, 3, device=DEV), torch.empty(batch, 4, device=DEV), None, None)
+    ms = timed(lambda i: engine.fk_jacobian_raw(topo, ee, table, q, want_jac=False, out=out), 20)
+    by = 4 * n + 28
+    res["fk_pose_only"] = {"ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
+                           "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK}
+    return res
+
+
 def bench_fk(model, link, batch):
     robot = O.load_robot(model.urdf_path if hasattr(model, "urdf_path") else model._urdf_path, torch.float32)
     n = robot.n_dofs
@@ -286,7 +309,8 @@ def main():
     out["config4_allegro_fk_jac"] = [bench_fk(allegro, "link_15.0_tip", b) for b in (32768, 1 << 21)]
     out["config5_kuka_train_step"] = [bench_train_step(b) for b in (131072,)]
     out["kuka_backward_kernels"] = [bench_backward_kernels(131072)]
-    out["kuka_forward_dynamics"] = [bench_forward_dynamics(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 20)]
+    out["kuka_kinematic_state"] = [bench_kinematic_state(drm.DifferentiableKUKAiiwa, 1 << 20)]
+    out["kuka_forward_dynamics"] =[bench_forward_dynamics(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 20)]
     print(json.dumps(out))
 
 
