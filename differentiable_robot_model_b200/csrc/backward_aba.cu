@@ -12,9 +12,12 @@
 //                       R1 leaves->root: reverse of F1 -> velocity adjoints, qd-bar
 //   every reverse pass adds its share of M-bar (-> q-bar, F-bar) and r-bar.
 //
-// Per link and configuration 69 floats stay in shared memory (slot-major): cos sin | w v | pA -> pA-bar |
-// IA (36) -> IA-bar | u | al a -> U-bar | adjoint accumulator (6) | d-bar u-bar | c-bar (4).  That footprint, not
-// arithmetic, sets the tile: 32 configurations per CTA for arm-sized models, 16 for the 29-link arm + hand.
+// Per link and configuration 33 floats stay in shared memory (slot-major): cos sin | w v | pA -> pA-bar | u |
+// al a -> U-bar | adjoint accumulator (6) | d-bar u-bar | c-bar (4).  The 6x6 articulated inertia IA_i (36 floats, later
+// overwritten by its adjoint) lives in a per-CTA slice of a GLOBAL scratch instead: the CTAs are persistent, so the whole
+// scratch is (#CTAs x links x 36 x 32 floats, 27 MB for the Kuka) and stays resident in the 126 MB L2; every access is a
+// coalesced 128-byte line of lane-private values.  With IA in shared memory (69 floats per link) only two single-warp CTAs
+// fit per SM -- two of the four schedulers idle; this layout runs four to five.
 // Table gradients: per-CTA accumulators in canonical frames, un-permuted into per-CTA partial tables, then the
 // fixed-order reduce kernel of backward.cu (deterministic, no atomics).
 #include "backward_common.cuh"
@@ -22,8 +25,9 @@
 namespace drm {
 
 constexpr float ABA_EPS_B = 1e-37f;
-constexpr int AL = 69;            // floats per link
-constexpr int O_CS = 0, O_W = 2, O_PA = 8, O_IA = 14, O_U = 50, O_AL = 51, O_ADJ = 57, O_DB = 63, O_UB = 64, O_CB = 65;
+constexpr int AL = 33;            // floats per link in shared memory (+ 36 per link in the L2-resident scratch)
+constexpr int O_CS = 0, O_W = 2, O_PA = 8, O_U = 14, O_AL = 15, O_ADJ = 21, O_DB = 27, O_UB = 28, O_CB = 29;
+constexpr int IA_FLOATS = 36;     // the 6x6 articulated inertia (-> its adjoint) of a link, global scratch
 
 struct AbaBwdArgs {
     const float* __restrict__ table;
@@ -35,6 +39,7 @@ struct AbaBwdArgs {
     float* __restrict__ qd_grad;
     float* __restrict__ f_grad;
     float* __restrict__ partials;
+    float* __restrict__ scratch;       // [grid][n_links - 1][36][T]: IA_i, later IA-bar_i (stays in L2)
     int64_t batch;
     uint32_t flags;
     int32_t vec_ok;
@@ -49,9 +54,9 @@ struct AbaBwdSmem {
         qd = o; o += T * n;
         f = o; o += T * n;
         g = o; o += T * n;
-        qg = o; o += T * n;
+        qg = g;                       // g_qdd_c is last read in R3 just before q-bar_c is first written
         qdg = o; o += T * n;
-        fg = o; o += T * n;
+        fg = f;                       // f is last read in F2, f-bar is written in R2
         o = (o + 3) & ~3;
         table = o; o += n_links * DRMB200_TABLE_STRIDE;
         link = o; o += (n_links - 1) * AL * T;
@@ -180,7 +185,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
         coop_copy(s_qd, args.qd + start * n, valid * n, vec_ok);
         coop_copy(s_f, args.f + start * n, valid * n, vec_ok);
         coop_copy(s_g, args.g_qdd + start * n, valid * n, vec_ok);
-        for (int i = tid; i < T * n; i += TB) { s_qg[i] = 0.f; s_qdg[i] = 0.f; s_fg[i] = 0.f; }
+        for (int i = tid; i < T * n; i += TB) s_qdg[i] = 0.f;      // q-bar and f-bar tiles alias inputs and are assigned, not accumulated
         __syncthreads();
 
         const bool active = tid < valid;
@@ -193,6 +198,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
         float* qdg = s_qdg + lane * n;
         float* fg = s_fg + lane * n;
         float* lk0 = s_link + lane - AL * T;            // link i lives at lk0 + i * AL * T   (i >= 1)
+        float* gia0 = args.scratch + ((int64_t)blockIdx.x * (N - 1) - 1) * IA_FLOATS * T + lane;     // IA of link i at gia0 + i * 36 * T
         const V3 zero = v3(0.f, 0.f, 0.f);
         const bool writer = tid < T;                    // shadows must not store
 
@@ -218,7 +224,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 Blocks I;
                 I.A = C.Io; I.B = skew_b(C.mc); I.C = transpose(I.B);
                 I.D = zero3(); I.D.a00 = I.D.a11 = I.D.a22 = C.m;
-                st_blocks(lk + O_IA * T, T, I);
+                st_blocks(gia0 + i * IA_FLOATS * T, T, I);
                 stv(lk + O_ADJ * T, T, zero); stv(lk + (O_ADJ + 3) * T, T, zero);
                 stv(lk + O_AL * T, T, zero); stv(lk + (O_AL + 3) * T, T, zero);
                 lk[O_DB * T] = 0.f; lk[O_UB * T] = 0.f; lk[O_U * T] = 0.f;
@@ -230,7 +236,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
             const int P = prog.parent[i];
             const int c = prog.dof[i];
             float* lk = lk0 + i * AL * T;
-            Blocks I = ld_blocks(lk + O_IA * T, T);
+            Blocks I = ld_blocks(gia0 + i * IA_FLOATS * T, T);
             V3 pa_ang = ldv(lk + O_PA * T, T), pa_lin = ldv(lk + (O_PA + 3) * T, T);
             V3 Ua = zero, Ul = zero;
             float d = 0.f, u = 0.f;
@@ -266,9 +272,9 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 const V3 q_ang = cross_add(r, q_lin, mul(M, pa_ang));
                 if (writer) {
                     float* pk = lk0 + P * AL * T;
-                    const Blocks Pk = ld_blocks(pk + O_IA * T, T);
+                    const Blocks Pk = ld_blocks(gia0 + P * IA_FLOATS * T, T);
                     Y.A = madd(Y.A, Pk.A); Y.B = madd(Y.B, Pk.B); Y.C = madd(Y.C, Pk.C); Y.D = madd(Y.D, Pk.D);
-                    st_blocks(pk + O_IA * T, T, Y);
+                    st_blocks(gia0 + P * IA_FLOATS * T, T, Y);
                     stv(pk + O_PA * T, T, ldv(pk + O_PA * T, T) + q_ang);
                     stv(pk + (O_PA + 3) * T, T, ldv(pk + (O_PA + 3) * T, T) + q_lin);
                 }
@@ -291,8 +297,8 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 const float qd_k = qdrow[c];
                 const V3 w = ldv(lk + O_W * T, T), v = ldv(lk + (O_W + 3) * T, T);
                 al = al + cross_z(w, qd_k); a = a + cross_z(v, qd_k);
-                const V3 Ua = v3(lk[(O_IA + 2) * T], lk[(O_IA + 5) * T], lk[(O_IA + 8) * T]);
-                const V3 Ul = v3(lk[(O_IA + 20) * T], lk[(O_IA + 23) * T], lk[(O_IA + 26) * T]);
+                const V3 Ua = v3(gia0[(i * IA_FLOATS + 2) * T], gia0[(i * IA_FLOATS + 5) * T], gia0[(i * IA_FLOATS + 8) * T]);
+                const V3 Ul = v3(gia0[(i * IA_FLOATS + 20) * T], gia0[(i * IA_FLOATS + 23) * T], gia0[(i * IA_FLOATS + 26) * T]);
                 const float qdd = (1.0f / Ua.z) * (lk[O_U * T] - (dot(Ua, al) + dot(Ul, a)));
                 al.z += qdd;
             }
@@ -316,8 +322,8 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 const V3 w = ldv(lk + O_W * T, T), v = ldv(lk + (O_W + 3) * T, T);
                 const V3 alq = mulT(M, alp) + cross_z(w, qd_k);
                 const V3 aq = mulT(M, cross_add(alp, r, ap)) + cross_z(v, qd_k);
-                const V3 Ua = v3(lk[(O_IA + 2) * T], lk[(O_IA + 5) * T], lk[(O_IA + 8) * T]);
-                const V3 Ul = v3(lk[(O_IA + 20) * T], lk[(O_IA + 23) * T], lk[(O_IA + 26) * T]);
+                const V3 Ua = v3(gia0[(i * IA_FLOATS + 2) * T], gia0[(i * IA_FLOATS + 5) * T], gia0[(i * IA_FLOATS + 8) * T]);
+                const V3 Ul = v3(gia0[(i * IA_FLOATS + 20) * T], gia0[(i * IA_FLOATS + 23) * T], gia0[(i * IA_FLOATS + 26) * T]);
                 const float dinv = 1.0f / Ua.z;
                 const float qdd = dinv * (lk[O_U * T] - (dot(Ua, alq) + dot(Ul, aq)));
                 const float k = (grow[c] + alq_b.z) * dinv;
@@ -342,7 +348,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
             M3 Mbar = zero3();
             add_outer(Mbar, cross_add(alp, r, ap), aq_b);
             add_outer(Mbar, alp, alq_b);
-            if (c >= 0 && writer) qg[c] += theta_grad_z(Mbar, M);
+            if (c >= 0 && writer) qg[c] = theta_grad_z(Mbar, M);     // first touch of q-bar_c (its tile aliases g_qdd, read above)
             if (NEED_TABLE) {
                 float vals[12];
                 if (c >= 0) rotate_z(Mbar, cs, -sn);
@@ -366,8 +372,8 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
             float db = 0.f, ub = 0.f;
             V3 Ua = zero, Ul = zero;
             if (c >= 0) {
-                Ua = v3(lk[(O_IA + 2) * T], lk[(O_IA + 5) * T], lk[(O_IA + 8) * T]);
-                Ul = v3(lk[(O_IA + 20) * T], lk[(O_IA + 23) * T], lk[(O_IA + 26) * T]);
+                Ua = v3(gia0[(i * IA_FLOATS + 2) * T], gia0[(i * IA_FLOATS + 5) * T], gia0[(i * IA_FLOATS + 8) * T]);
+                Ul = v3(gia0[(i * IA_FLOATS + 20) * T], gia0[(i * IA_FLOATS + 23) * T], gia0[(i * IA_FLOATS + 26) * T]);
                 Uab = ldv(lk + O_AL * T, T); Ulb = ldv(lk + (O_AL + 3) * T, T);
                 db = lk[O_DB * T]; ub = lk[O_UB * T];
             }
@@ -379,10 +385,10 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 load_Fr(s_tab + i * DRMB200_TABLE_STRIDE, M, r);
                 if (c >= 0) rotate_z(M, cs, sn);
                 const float* pk = lk0 + P * AL * T;
-                const Blocks Y = ld_blocks(pk + O_IA * T, T);                     // IA-bar of the parent
+                const Blocks Y = ld_blocks(gia0 + P * IA_FLOATS * T, T);                     // IA-bar of the parent
                 const V3 Qa_b = ldv(pk + O_PA * T, T), Ql_b = ldv(pk + (O_PA + 3) * T, T);
                 // recompute IA', pa of this link
-                Blocks I = ld_blocks(lk + O_IA * T, T);
+                Blocks I = ld_blocks(gia0 + i * IA_FLOATS * T, T);
                 V3 pa_ang = ldv(lk + O_PA * T, T), pa_lin = ldv(lk + (O_PA + 3) * T, T);
                 float inv = 0.f, u = 0.f;
                 V3 ca = zero, cl = zero;
@@ -466,7 +472,7 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
                 Ib.C.a02 += Ulb.x; Ib.C.a12 += Ulb.y; Ib.C.a22 += Ulb.z;
             }
             if (writer) {
-                st_blocks(lk + O_IA * T, T, Ib);                                    // IA_i is dead: keep IA-bar_i for the children
+                st_blocks(gia0 + i * IA_FLOATS * T, T, Ib);                                    // IA_i is dead: keep IA-bar_i for the children
                 stv(lk + O_PA * T, T, pb_ang); stv(lk + (O_PA + 3) * T, T, pb_lin);
             }
             if (NEED_TABLE) {
@@ -551,6 +557,15 @@ aba_backward_kernel(const __grid_constant__ TreeProgram prog, const AbaBwdArgs a
     }
 }
 
+// workspace = per-CTA partial tables (as for the other backward kernels) + the per-CTA articulated-inertia scratch
+int64_t forward_dynamics_backward_workspace_bytes(const drmb200_topology_t* topo, int64_t batch) {
+    if (topo == nullptr || topo->n_links < 1 || topo->n_links > DRMB200_MAX_LINKS) return 0;
+    int64_t tiles = (batch + 15) / 16;
+    if (tiles < 1) tiles = 1;
+    const int64_t grid = tiles < BWD_MAX_GRID ? tiles : BWD_MAX_GRID;
+    return table_grad_workspace_bytes(topo, batch) + grid * (topo->n_links - 1) * IA_FLOATS * 32 * (int64_t)sizeof(float);
+}
+
 int forward_dynamics_backward_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
                                      const float* f, int64_t batch, uint32_t flags, const float* g_qdd,
                                      float* q_grad, float* qd_grad, float* f_grad, float* table_grad, void* workspace,
@@ -562,12 +577,14 @@ int forward_dynamics_backward_device(const drmb200_topology_t* topo, const float
     if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
     if (q_grad == nullptr && qd_grad == nullptr && f_grad == nullptr && table_grad == nullptr) return DRMB200_OK;
     if (table == nullptr || q == nullptr || qd == nullptr || f == nullptr || g_qdd == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
-    if (table_grad != nullptr && workspace == nullptr) { set_error("table_grad requested without workspace"); return DRMB200_EINVAL; }
+    if (workspace == nullptr) { set_error("forward-dynamics backward needs its workspace (drmb200_forward_dynamics_backward_workspace_bytes)"); return DRMB200_EINVAL; }
 
     AbaBwdArgs args;
     args.table = table; args.q = q; args.qd = qd; args.f = f; args.g_qdd = g_qdd;
     args.q_grad = q_grad; args.qd_grad = qd_grad; args.f_grad = f_grad;
-    args.partials = static_cast<float*>(workspace); args.batch = batch; args.flags = flags;
+    args.partials = static_cast<float*>(workspace);
+    args.scratch = reinterpret_cast<float*>(static_cast<char*>(workspace) + table_grad_workspace_bytes(topo, batch));
+    args.batch = batch; args.flags = flags;
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.vec_ok = (al16(q) && al16(qd) && al16(f) && al16(g_qdd) && al16(q_grad) && al16(qd_grad) && al16(f_grad)) ? 1 : 0;
 

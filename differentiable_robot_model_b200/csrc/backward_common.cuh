@@ -110,6 +110,8 @@ static int persistent_grid(Kern kern, int block, size_t smem_bytes, int64_t tile
 }
 
 
+int64_t table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch);     // backward.cu
+
 // sums the per-CTA partial tables in fixed order and adds them to table_grad (defined in backward.cu)
 int launch_reduce(const float* partials, int grid, const drmb200_topology_t* topo, float* table_grad, cudaStream_t stream);
 

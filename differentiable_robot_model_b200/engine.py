@@ -47,6 +47,7 @@ _SIGNATURES = {
     "drmb200_forward_dynamics": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                 ctypes.c_void_p]),
+    "drmb200_forward_dynamics_backward_workspace_bytes": (ctypes.c_int64, [ctypes.POINTER(Topology), ctypes.c_int64]),
     "drmb200_forward_dynamics_backward": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                          _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                          _c_float_p, _c_float_p, _c_float_p, _c_float_p,
@@ -317,7 +318,8 @@ class ForwardDynamicsFunction(torch.autograd.Function):
         q_grad = torch.empty_like(q) if need[1] else None
         qd_grad = torch.empty_like(q) if need[2] else None
         f_grad = torch.empty_like(q) if need[3] else None
-        ws = _workspace(ctx.topo, B, q.device)
+        nbytes = int(lib().drmb200_forward_dynamics_backward_workspace_bytes(ctypes.byref(ctx.topo), B))
+        ws = torch.empty((nbytes + 3) // 4, device=q.device, dtype=torch.float32)
         with torch.cuda.device(q.device):
             rc = lib().drmb200_forward_dynamics_backward(
                 ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B, ctx.flags, _ptr(g_qdd), _ptr(q_grad), _ptr(qd_grad),

@@ -150,9 +150,11 @@ int drmb200_forward_dynamics(const drmb200_topology_t* topo,
 /*
  * Adjoint of drmb200_forward_dynamics given g_qdd [B, n_dofs] (the reference differentiates its op graph with
  * autograd; this is the analytic reverse-mode recursion, exact also for non-symmetric inertia matrices).  Any of
- * q_grad / qd_grad / f_grad [B, n_dofs] and table_grad [n_links, 28] may be NULL; table_grad is accumulated into and
- * needs `workspace` of drmb200_table_grad_workspace_bytes() bytes.
+ * q_grad / qd_grad / f_grad [B, n_dofs] and table_grad [n_links, 28] may be NULL; table_grad is accumulated into.
+ * `workspace` (always required) must hold drmb200_forward_dynamics_backward_workspace_bytes() bytes: the per-CTA partial
+ * tables plus an L2-resident scratch for the 6x6 articulated inertias of the persistent CTAs.
  */
+int64_t drmb200_forward_dynamics_backward_workspace_bytes(const drmb200_topology_t* topo, int64_t batch);
 int drmb200_forward_dynamics_backward(const drmb200_topology_t* topo,
                                       const float* table, const float* q, const float* qd, const float* f,
                                       int64_t batch, uint32_t flags, const float* g_qdd,

@@ -111,8 +111,8 @@ def bench_forward_dynamics(stem_cls, batch):
            "forward_achieved_GBps": batch * 16 * n / ms / 1e6}
     g = torch.randn(batch, n, device=DEV)
     qg, qdg, fg, tg = torch.empty_like(g), torch.empty_like(g), torch.empty_like(g), torch.zeros_like(table)
-    ws = engine._workspace(topo, batch, DEV)
     lib, P, S = engine.lib(), engine._ptr, engine._stream
+    ws = torch.empty(int(lib.drmb200_forward_dynamics_backward_workspace_bytes(ctypes.byref(topo), batch)) // 4 + 1, device=DEV)
 
     def bwd(with_table):
         rc = lib.drmb200_forward_dynamics_backward(ctypes.byref(topo), P(table), P(sets[0][0]), P(sets[0][1]), P(fs[0]), batch, 3,
