@@ -65,3 +65,16 @@ def test_exp_map_matches_matrix_exponential():
     w = torch.tensor([0.3, -0.7, 0.5])
     hat = torch.tensor([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
     np.testing.assert_allclose(P.exp_map_so3(w).numpy(), torch.linalg.matrix_exp(hat).numpy(), atol=1e-6)
+
+
+def test_utils_helpers_match_reference_semantics():
+    from differentiable_robot_model_b200 import utils as U
+    a, b = torch.tensor([[1.0, 2.0, 3.0], [0.5, -1.0, 2.0]]), torch.tensor([[0.3, -0.2, 0.9], [1.0, 1.0, 1.0]])
+    np.testing.assert_allclose(U.cross_product(a, b).numpy(), torch.linalg.cross(a, b).numpy(), atol=1e-6)
+    S = U.vector3_to_skew_symm_matrix(a[0])
+    assert S.shape == (1, 3, 3) and torch.equal(S, -S.transpose(1, 2))
+    A = U.bfill_diagonal(U.bfill_lowertriangle(torch.zeros(2, 3, 3), torch.tensor([1.0, 2.0, 3.0])), torch.tensor([7.0, 8.0, 9.0]))
+    assert A[1, 1, 0] == 1 and A[1, 2, 0] == 2 and A[1, 2, 1] == 3 and A[0, 2, 2] == 9 and A[0, 0, 1] == 0
+    assert U.convert_into_at_least_2d_pytorch_tensor([1.0, 2.0]).shape == (1, 2)
+    w = torch.tensor([0.3, -0.7, 0.5])
+    np.testing.assert_allclose(U.exp_map_so3(w).numpy(), P.exp_map_so3(w).numpy(), atol=1e-7)
