@@ -14,8 +14,10 @@ constexpr float GRAVITY_B = 9.81f;
 // Transposed, two stages, fixed order (deterministic): every thread drops its NV <= 32 values into a padded scratch
 // matrix; in each warp lane j adds up value j of the warp's 32 threads (32 independent conflict-free loads, four
 // interleaved add chains -- no serial shuffle trees, whose latency these low-occupancy kernels cannot hide); warp 0
-// then adds the per-warp partials.  Scratch: block_accumulate_floats(NV, T) floats.
-__host__ __device__ constexpr int block_accumulate_floats(int nv, int t) { return nv * (t + 1) + (t / 32) * 32; }
+// then adds the per-warp partials.  Scratch: block_accumulate_floats(NV, T) floats, laid out [per-warp partials | values];
+// the partials sit at a FIXED offset so that calls with different NV sharing one scratch cannot have a late reader of the
+// partials overlap an early writer of the next call's values (racecheck-clean, scripts/gpu_sanitize.sh).
+__host__ __device__ constexpr int block_accumulate_floats(int nv, int t) { return (t / 32) * 32 + nv * (t + 1); }
 
 template <int NV, int T, typename Map>
 __device__ __forceinline__ void block_accumulate(float* scratch, float* acc_row, const float (&vals)[NV], bool active,
@@ -23,14 +25,15 @@ __device__ __forceinline__ void block_accumulate(float* scratch, float* acc_row,
     static_assert(NV <= 32 && T % 32 == 0, "one lane per value");
     constexpr int SCR_LD = T + 1;             // padded leading dimension of the reduction scratch
     constexpr int NW = T / 32;
-    float* partial = scratch + NV * SCR_LD;   // [NW][32]
+    float* partial = scratch;                 // [NW][32]
+    float* values = scratch + NW * 32;        // [NV][SCR_LD]
     const int tid = threadIdx.x;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) scratch[j * SCR_LD + tid] = active ? vals[j] : 0.f;
+    for (int j = 0; j < NV; ++j) values[j * SCR_LD + tid] = active ? vals[j] : 0.f;
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
     if (lane < NV) {
-        const float* row = scratch + lane * SCR_LD + warp * 32;
+        const float* row = values + lane * SCR_LD + warp * 32;
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
         for (int c = 0; c < 32; c += 4) { s0 += row[c]; s1 += row[c + 1]; s2 += row[c + 2]; s3 += row[c + 3]; }
