@@ -67,6 +67,7 @@ int forward_dynamics_backward_device(const drmb200_topology_t*, const float*, co
                                      int64_t, uint32_t, const float*, float*, float*, float*, float*, void*, cudaStream_t);
 int64_t table_grad_workspace_bytes(const drmb200_topology_t*, int64_t);
 int64_t forward_dynamics_backward_workspace_bytes(const drmb200_topology_t*, int64_t);
+int mass_matrix_device(const drmb200_topology_t*, const float*, const float*, int64_t, float*, cudaStream_t);
 int build_table_device(const float*, int32_t, float*, cudaStream_t);
 int kinematic_state_device(const drmb200_topology_t*, const float*, const float*, const float*, int64_t, float*, float*,
                            float*, cudaStream_t);
@@ -252,6 +253,11 @@ int drmb200_forward_dynamics(const drmb200_topology_t* topo, const float* table,
                              const float* f, int64_t batch, uint32_t flags, float* qdd, void* cuda_stream) {
     return drm::forward_dynamics_device(topo, table, q, qd, f, batch, flags, qdd,
                                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_mass_matrix(const drmb200_topology_t* topo, const float* table, const float* q, int64_t batch, float* H,
+                        void* cuda_stream) {
+    return drm::mass_matrix_device(topo, table, q, batch, H, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int64_t drmb200_forward_dynamics_backward_workspace_bytes(const drmb200_topology_t* topo, int64_t batch) {

@@ -47,6 +47,8 @@ _SIGNATURES = {
     "drmb200_forward_dynamics": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                 ctypes.c_void_p]),
+    "drmb200_mass_matrix": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, ctypes.c_int64, _c_float_p,
+                                           ctypes.c_void_p]),
     "drmb200_forward_dynamics_backward_workspace_bytes": (ctypes.c_int64, [ctypes.POINTER(Topology), ctypes.c_int64]),
     "drmb200_forward_dynamics_backward": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                          _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
@@ -326,3 +328,51 @@ class ForwardDynamicsFunction(torch.autograd.Function):
                 _ptr(f_grad), _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_forward_dynamics_backward")
         return table_grad, q_grad, qd_grad, f_grad, None, None
+
+
+def mass_matrix_raw(topo, table, q, out=None):
+    """Joint-space inertia matrix [B, n, n], one launch (drmb200_mass_matrix)."""
+    _require_cuda(table, q)
+    q = q.contiguous()
+    B, n = q.shape
+    H = out if out is not None else torch.empty((B, n, n), device=q.device, dtype=torch.float32)
+    with torch.cuda.device(q.device):
+        rc = lib().drmb200_mass_matrix(ctypes.byref(topo), _ptr(table), _ptr(q), B, _ptr(H), _stream())
+    _check(rc, "drmb200_mass_matrix")
+    return H
+
+
+class MassMatrixFunction(torch.autograd.Function):
+    """(table, q) -> H [B, n, n].  Forward: the mass-matrix kernel.  Backward: column j of H is the inverse-dynamics
+    torque for (q, qd = 0, qdd = e_j) without gravity or damping, so the adjoint is ONE launch of the RNEA adjoint
+    kernel over the n stacked unit-acceleration batches (q_grad summed over the stack, table_grad as is)."""
+
+    @staticmethod
+    def forward(ctx, table, q, topo):
+        table, q = table.contiguous(), q.contiguous()
+        H = mass_matrix_raw(topo, table, q)
+        ctx.save_for_backward(table, q)
+        ctx.topo = topo
+        return H
+
+    @staticmethod
+    def backward(ctx, g_H):
+        table, q = ctx.saved_tensors
+        need_table, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        B, n = q.shape
+        _require_cuda(g_H)
+        qs = q.repeat(n, 1)                                            # slab j = the batch with qdd = e_j
+        zeros = torch.zeros_like(qs)
+        qdd = zeros.view(n, B, n).clone()
+        idx = torch.arange(n, device=q.device)
+        qdd[idx, :, idx] = 1.0
+        g_tau = g_H.permute(2, 0, 1).contiguous().view(n * B, n)       # slab j: dL/dH[:, :, j]
+        table_grad = torch.zeros_like(table) if need_table else None
+        q_grad = torch.empty_like(qs) if need_q else None
+        ws = _workspace(ctx.topo, n * B, q.device)
+        with torch.cuda.device(q.device):
+            rc = lib().drmb200_inverse_dynamics_backward(
+                ctypes.byref(ctx.topo), _ptr(table), _ptr(qs), _ptr(zeros), _ptr(qdd.view(n * B, n)), n * B, 0, _ptr(g_tau),
+                _ptr(q_grad), None, None, _ptr(table_grad), _ptr(ws), _stream())
+        _check(rc, "drmb200_inverse_dynamics_backward")
+        return table_grad, (q_grad.view(n, B, n).sum(0) if need_q else None), None

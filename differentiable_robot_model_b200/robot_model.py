@@ -274,9 +274,24 @@ class DifferentiableRobotModel(torch.nn.Module):
         include_gravity: Optional[bool] = True,
         use_damping: Optional[bool] = True,
     ) -> torch.Tensor:
-        r"""Joint-space mass matrix ``H(q)`` ``[batch_size x n_dofs x n_dofs]``.  Same construction as the reference
-        (``robot_model.py:403-450``: column j = ID(q, 0, e_j) - ID(q, 0, 0)), but as ONE RNEA launch over a
-        ``(n_dofs + 1) x batch`` stacked batch instead of n+1 walks of the per-link op graph."""
+        r"""Joint-space mass matrix ``H(q)`` ``[batch_size x n_dofs x n_dofs]`` in ONE launch (``csrc/mass_matrix.cu``).
+        The reference builds it from n + 1 inverse-dynamics evaluations (``robot_model.py:403-450``: column j =
+        ID(q, 0, e_j) - ID(q, 0, 0)); the subtraction cancels gravity and damping (qd = 0), so the kernel evaluates the n
+        unit-acceleration columns directly for zero velocity and zero gravity -- ``include_gravity`` / ``use_damping``
+        therefore do not change the result, exactly as in the reference up to its fp32 cancellation noise.
+        Differentiable w.r.t. q and every learnable link parameter (RNEA adjoint kernel over the stacked columns)."""
+        assert q.shape[1] == self._n_dofs
+        return engine.MassMatrixFunction.apply(self._link_table(), q, self._topology)
+
+    @tensor_check
+    def compute_lagrangian_inertia_matrix_stacked(
+        self,
+        q: torch.Tensor,
+        include_gravity: Optional[bool] = True,
+        use_damping: Optional[bool] = True,
+    ) -> torch.Tensor:
+        r"""The reference's construction verbatim (column j = ID(q, 0, e_j) - ID(q, 0, 0)) as ONE RNEA launch over a
+        ``(n_dofs + 1) x batch`` stacked batch; kept as an independent cross-check of the mass-matrix kernel."""
         assert q.shape[1] == self._n_dofs
         B, n = q.shape
         zero = q.new_zeros((n + 1) * B, n)

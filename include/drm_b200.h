@@ -138,6 +138,15 @@ int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo,
                                       float* table_grad, void* workspace, void* cuda_stream);
 
 /*
+ * Joint-space inertia matrix H [B, n_dofs, n_dofs] (row-major per configuration): replaces
+ * compute_lagrangian_inertia_matrix (robot_model.py:403-450; there n_dofs + 1 inverse-dynamics evaluations whose
+ * difference cancels gravity and damping) with ONE launch that evaluates the n_dofs unit-acceleration columns
+ * H[:, :, j] = ID(q, 0, e_j) - ID(q, 0, 0) for zero velocity and zero gravity.
+ */
+int drmb200_mass_matrix(const drmb200_topology_t* topo, const float* table, const float* q, int64_t batch,
+                        float* H, void* cuda_stream);
+
+/*
  * Articulated-body forward dynamics, qdd [B, n_dofs] from applied joint forces f [B, n_dofs]: replaces
  * compute_forward_dynamics (robot_model.py:488-624) in one launch, with the reference's arithmetic (general 6x6
  * articulated inertias, U = IA S used as a column, +1e-37 regularisers).  flags = DRMB200_GRAVITY | DRMB200_DAMPING

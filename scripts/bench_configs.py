@@ -174,6 +174,22 @@ def bench_kinematic_state(stem_cls, batch):
     return res
 
 
+def bench_mass_matrix(stem_cls, batch):
+    """One-launch mass-matrix kernel vs the reference's construction through the RNEA kernel ((n + 1) x batch stacked)."""
+    m = stem_cls(device=DEV)
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    n = robot.n_dofs
+    q = O.sample_inputs(robot, batch, seed=0)[0].to(DEV)
+    table, topo = m._link_table(), m._topology
+    out = torch.empty(batch, n, n, device=DEV)
+    ms = timed(lambda i: engine.mass_matrix_raw(topo, table, q, out=out), 200 if batch <= (1 << 17) else 20)
+    with torch.no_grad():
+        ms_stacked = timed(lambda i: m.compute_lagrangian_inertia_matrix_stacked(q), 20)
+    by = 4 * n + 4 * n * n
+    return {"batch": batch, "kernel_ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
+            "achieved_GBps": batch * by / ms / 1e6, "stacked_rnea_ms": ms_stacked}
+
+
 def bench_fk(model, link, batch):
     robot = O.load_robot(model.urdf_path if hasattr(model, "urdf_path") else model._urdf_path, torch.float32)
     n = robot.n_dofs
@@ -309,6 +325,7 @@ def main():
     out["config4_allegro_fk_jac"] = [bench_fk(allegro, "link_15.0_tip", b) for b in (32768, 1 << 21)]
     out["config5_kuka_train_step"] = [bench_train_step(b) for b in (131072,)]
     out["kuka_backward_kernels"] = [bench_backward_kernels(131072)]
+    out["kuka_mass_matrix"] = [bench_mass_matrix(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 20)]
     out["kuka_kinematic_state"] = [bench_kinematic_state(drm.DifferentiableKUKAiiwa, 1 << 20)]
     out["kuka_forward_dynamics"] =[bench_forward_dynamics(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 20)]
     print(json.dumps(out))
