@@ -386,6 +386,13 @@ def main():
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
     if not args.no_e2e:
         e2e_steps = max(3, min(args.steps, 200))
+        numa_bound = False
+        if world > 1 and os.environ.get("DRMB200_BENCH_NUMA_BIND", "1") != "0":
+            # one process per GPU: keep this rank's page-locked buffers on the NUMA node of its GPU
+            from differentiable_robot_model_b200.parallel import bind_to_device_numa_node
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+            numa_bound = bind_to_device_numa_node(phys)
         q_host = [qs[i].cpu().pin_memory() for i in range(2)]
         host_out = [(torch.empty(BATCH, 3).pin_memory(), torch.empty(BATCH, 4).pin_memory(),
                      torch.empty(BATCH, 3, N_DOF).pin_memory(), torch.empty(BATCH, 3, N_DOF).pin_memory())
@@ -405,6 +412,7 @@ def main():
         result["e2e"] = {"value": world * e2e_steps * BATCH / float(dt.item()), "unit": UNIT,
                          "h2d_bytes_per_step": BATCH * 4 * N_DOF, "d2h_bytes_per_step": BATCH * (28 + 24 * N_DOF),
                          "steps": e2e_steps, "api": "drmb200_fk_jacobian_host (pinned host buffers in and out)",
+                         "numa_bound": numa_bound,
                          "transfer": "fused: one launch per step, the kernel's TMA bulk copies read q from and write all "
                                      "outputs to the pinned HOST buffers over PCIe (no staging copies); the bytes below "
                                      "cross PCIe inside the timed region every step",

@@ -66,3 +66,20 @@ def allreduce_link_param_grads(model) -> int:
         p.grad.copy_(flat[off:off + n].view_as(p.grad))
         off += n
     return off
+
+
+def bind_to_device_numa_node(device_index: int) -> bool:
+    """Pin the calling process to the CPU cores closest to GPU ``device_index`` (NVML's ideal affinity).
+
+    One process per GPU with host buffers on the box (``drmb200_fk_jacobian_host``): the page-locked buffers should
+    live on the NUMA node the GPU's PCIe root hangs off, otherwise every tile crosses the socket interconnect and
+    the ranks contend for it.  Call this BEFORE allocating (first-touching) pinned buffers.  Returns False, changing
+    nothing, when NVML is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:
+        return False
