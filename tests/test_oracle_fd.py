@@ -113,3 +113,23 @@ def test_forward_dynamics_adjoint_recursions_match_autograd(stem):
                 continue
             a = torch.zeros_like(b) if a is None else a
             assert rel(a, b) < 1e-9, (stem, grav, damp)
+
+
+def test_mass_matrix_construction_matches_reference(robot_stem):
+    """Column j = ID(q, 0, e_j) - ID(q, 0, 0) through the oracle's inverse dynamics vs the reference's
+    compute_lagrangian_inertia_matrix (robot_model.py:403-450); the reference's fp32 subtraction of the gravity terms
+    leaves noise of ~1e-6 x the gravity torque, hence the absolute floor."""
+    g = load_fd(robot_stem)
+    robot = O.load_robot(urdf_path(robot_stem), torch.float64)
+    q = torch.tensor(g["q"], dtype=torch.float64)
+    z = torch.zeros_like(q)
+    cols = []
+    for j in range(robot.n_dofs):
+        e = z.clone()
+        e[:, j] = 1
+        cols.append(O.inverse_dynamics(robot, q, z, e, False, False))
+    H = torch.stack(cols, dim=2).numpy()
+    grav = np.abs(O.inverse_dynamics(robot, q, z, z, True, False).numpy()).max()
+    for key in ("H.g1d1", "H.g0d0"):
+        floor = 2e-5 * np.abs(g[key]).max() + (4e-6 * grav if key == "H.g1d1" else 0.0)
+        assert np.all(np.abs(H - g[key]) <= 2e-4 * np.abs(g[key]) + floor), key
