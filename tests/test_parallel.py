@@ -86,3 +86,12 @@ def test_world_size_2_gloo(tmp_path):
     world, port = 2, _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert sorted(os.listdir(tmp_path)) == ["ok0", "ok1"]
+
+
+def test_numa_binding_is_a_safe_no_op_without_nvml():
+    """No GPU / NVML in the CPU container: the helper must report False and leave the affinity alone."""
+    import os
+    before = os.sched_getaffinity(0)
+    assert parallel.bind_to_device_numa_node(0) in (False, True)
+    if not torch.cuda.is_available():
+        assert os.sched_getaffinity(0) == before
