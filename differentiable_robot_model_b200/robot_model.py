@@ -265,7 +265,8 @@ class DifferentiableRobotModel(torch.nn.Module):
         return self.compute_inverse_dynamics(q, qd, q.new_zeros(q.shape), include_gravity, use_damping)
 
     # ------------------------------------------------------------------------------------------
-    # callers of the hot path (SURVEY.md section 8f "next" rows) -- thin compositions of the RNEA / FK kernels
+    # callers either side of the hot path (SURVEY.md section 8f "next" rows): mass matrix, forward dynamics and
+    # all-links kinematics each have their own kernel; non-linear effects is the RNEA kernel with qdd = 0
     # ------------------------------------------------------------------------------------------
     @tensor_check
     def compute_lagrangian_inertia_matrix(
