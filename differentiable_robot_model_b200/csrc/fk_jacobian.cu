@@ -86,6 +86,99 @@ __device__ __forceinline__ void walk_link(const float* row, const float* qrow, i
     }
 }
 
+// Two configurations per thread: rows `a` and `b` of the tile ride in the two lanes of packed FP32x2 registers, so EVERY
+// arithmetic instruction of the chain walk (R r~, R F~, the axis cross products, Rz) is one FFMA2 / FMUL2 for two
+// configurations, and table loads, loop control and addressing are shared.  Link-table operands are scalar broadcasts.
+// sincos and the quaternion (per-lane branches, integer quadrant logic) run per lane.
+__device__ __forceinline__ f32x2 neg2(f32x2 x) { return mul2(x, bc2(-1.f)); }
+
+template <bool WITH_JAC>
+__device__ __forceinline__ void pair_walk(const PathProgram& prog, const FkArgs& args, int n, int len, int a, int b,
+                                          const float* s_q, float* s_pos, float* s_quat, float* s_jlin, float* s_jang,
+                                          const float* s_tab) {
+    f32x2 R00 = pk2(1.f, 1.f), R01 = pk2(0.f, 0.f), R02 = R01, R10 = R01, R11 = R00, R12 = R01, R20 = R01, R21 = R01, R22 = R00;
+    f32x2 px = R01, py = R01, pz = R01;
+    const float* qa = s_q + a * n;
+    const float* qb = s_q + b * n;
+    float* jla = s_jlin + a * 3 * n; float* jlb = s_jlin + b * 3 * n;
+    float* jaa = s_jang + a * 3 * n; float* jab = s_jang + b * 3 * n;
+    for (int k = 0; k < len; ++k) {
+        M3 F; V3 r;
+        load_Fr(s_tab + k * 12, F, r);
+        // p_i = R_parent r_i + p_parent
+        px = fma2(R00, bc2(r.x), fma2(R01, bc2(r.y), fma2(R02, bc2(r.z), px)));
+        py = fma2(R10, bc2(r.x), fma2(R11, bc2(r.y), fma2(R12, bc2(r.z), py)));
+        pz = fma2(R20, bc2(r.x), fma2(R21, bc2(r.y), fma2(R22, bc2(r.z), pz)));
+        // R_parent F~_i  (same association order as mul(M3, M3))
+        const f32x2 G00 = fma2(R00, bc2(F.a00), fma2(R01, bc2(F.a10), mul2(R02, bc2(F.a20))));
+        const f32x2 G01 = fma2(R00, bc2(F.a01), fma2(R01, bc2(F.a11), mul2(R02, bc2(F.a21))));
+        const f32x2 G02 = fma2(R00, bc2(F.a02), fma2(R01, bc2(F.a12), mul2(R02, bc2(F.a22))));
+        const f32x2 G10 = fma2(R10, bc2(F.a00), fma2(R11, bc2(F.a10), mul2(R12, bc2(F.a20))));
+        const f32x2 G11 = fma2(R10, bc2(F.a01), fma2(R11, bc2(F.a11), mul2(R12, bc2(F.a21))));
+        const f32x2 G12 = fma2(R10, bc2(F.a02), fma2(R11, bc2(F.a12), mul2(R12, bc2(F.a22))));
+        const f32x2 G20 = fma2(R20, bc2(F.a00), fma2(R21, bc2(F.a10), mul2(R22, bc2(F.a20))));
+        const f32x2 G21 = fma2(R20, bc2(F.a01), fma2(R21, bc2(F.a11), mul2(R22, bc2(F.a21))));
+        const f32x2 G22 = fma2(R20, bc2(F.a02), fma2(R21, bc2(F.a12), mul2(R22, bc2(F.a22))));
+        R00 = G00; R01 = G01; R02 = G02; R10 = G10; R11 = G11; R12 = G12; R20 = G20; R21 = G21; R22 = G22;
+        const int c = prog.dof[k];
+        if (c >= 0) {
+            float sa, ca, sb, cb;
+            sincos_pi2(qa[c], sa, ca);
+            sincos_pi2(qb[c], sb, cb);
+            const f32x2 cs = pk2(ca, cb), sn = pk2(sa, sb), nsn = pk2(-sa, -sb);
+            if (WITH_JAC) {
+                // z = third column (unchanged by Rz); park z in J_ang (final) and p_i x z = -(z x p_i) in J_lin
+                const f32x2 mx = fma2(py, R22, neg2(mul2(pz, R12)));
+                const f32x2 my = fma2(pz, R02, neg2(mul2(px, R22)));
+                const f32x2 mz = fma2(px, R12, neg2(mul2(py, R02)));
+                float lo, hi;
+                upk2(R02, lo, hi); jaa[c] = lo; jab[c] = hi;
+                upk2(R12, lo, hi); jaa[n + c] = lo; jab[n + c] = hi;
+                upk2(R22, lo, hi); jaa[2 * n + c] = lo; jab[2 * n + c] = hi;
+                upk2(mx, lo, hi); jla[c] = lo; jlb[c] = hi;
+                upk2(my, lo, hi); jla[n + c] = lo; jlb[n + c] = hi;
+                upk2(mz, lo, hi); jla[2 * n + c] = lo; jlb[2 * n + c] = hi;
+            }
+            // R <- R Rz(q): col0' = c col0 + s col1, col1' = -s col0 + c col1
+            const f32x2 t0 = fma2(cs, R00, mul2(sn, R01)), t1 = fma2(cs, R10, mul2(sn, R11)), t2 = fma2(cs, R20, mul2(sn, R21));
+            R01 = fma2(cs, R01, mul2(nsn, R00)); R11 = fma2(cs, R11, mul2(nsn, R10)); R21 = fma2(cs, R21, mul2(nsn, R20));
+            R00 = t0; R10 = t1; R20 = t2;
+        }
+    }
+    if (WITH_JAC) {
+        // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee + (p_i x z)      (robot_model.py:661)
+        const f32x2 npx = neg2(px), npy = neg2(py), npz = neg2(pz);
+        for (int k = 0; k < len; ++k) {
+            const int c = prog.dof[k];
+            if (c < 0) continue;
+            const f32x2 zx = pk2(jaa[c], jab[c]), zy = pk2(jaa[n + c], jab[n + c]), zz = pk2(jaa[2 * n + c], jab[2 * n + c]);
+            const f32x2 mx = pk2(jla[c], jlb[c]), my = pk2(jla[n + c], jlb[n + c]), mz = pk2(jla[2 * n + c], jlb[2 * n + c]);
+            const f32x2 jx = fma2(zy, pz, fma2(zz, npy, mx));
+            const f32x2 jy = fma2(zz, px, fma2(zx, npz, my));
+            const f32x2 jz = fma2(zx, py, fma2(zy, npx, mz));
+            float lo, hi;
+            upk2(jx, lo, hi); jla[c] = lo; jlb[c] = hi;
+            upk2(jy, lo, hi); jla[n + c] = lo; jlb[n + c] = hi;
+            upk2(jz, lo, hi); jla[2 * n + c] = lo; jlb[2 * n + c] = hi;
+        }
+    }
+    M3 Ra, Rb;
+    upk2(R00, Ra.a00, Rb.a00); upk2(R01, Ra.a01, Rb.a01); upk2(R02, Ra.a02, Rb.a02);
+    upk2(R10, Ra.a10, Rb.a10); upk2(R11, Ra.a11, Rb.a11); upk2(R12, Ra.a12, Rb.a12);
+    upk2(R20, Ra.a20, Rb.a20); upk2(R21, Ra.a21, Rb.a21); upk2(R22, Ra.a22, Rb.a22);
+    if (args.pos != nullptr) {
+        float lo, hi;
+        upk2(px, lo, hi); s_pos[a * 3] = lo; s_pos[b * 3] = hi;
+        upk2(py, lo, hi); s_pos[a * 3 + 1] = lo; s_pos[b * 3 + 1] = hi;
+        upk2(pz, lo, hi); s_pos[a * 3 + 2] = lo; s_pos[b * 3 + 2] = hi;
+    }
+    if (args.quat != nullptr) {
+        if (prog.ee_axis != 0) { Ra = unpermute_cols(Ra, prog.ee_axis); Rb = unpermute_cols(Rb, prog.ee_axis); }
+        reinterpret_cast<float4*>(s_quat)[a] = quat_xyzw(Ra);
+        reinterpret_cast<float4*>(s_quat)[b] = quat_xyzw(Rb);
+    }
+}
+
 // MAXLEN > 0: paths of at most MAXLEN links, loops fully unrolled, the Jacobian columns (z_i, z_i x p_i)
 //             wait in REGISTERS for p_ee and are written to the smem tile exactly once;
 // MAXLEN = 0: any path length, rolled loop, columns parked in the smem tile and fixed up in a second pass.
@@ -139,7 +232,12 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
     if (bulk) mbar_wait(&mbar, 0);
 
     // ---- chain walk ----------------------------------------------------------------------------
-    if (tid < valid) {
+    if (MAXLEN == -2) {
+        // two configurations per thread: rows tid and tid + TILE/2 (row strides stay odd -> conflict-free); the upper
+        // half of the CTA only helps with staging.  A ragged tail may leave lane b on an unused row: computed, never copied.
+        if (tid < TILE / 2 && tid < valid)
+            pair_walk<WITH_JAC>(prog, args, n, len, tid, tid + TILE / 2, s_q, s_pos, s_quat, s_jlin, s_jang, s_tab);
+    } else if (tid < valid) {
         M3 R = identity3();
         V3 p = v3(0.f, 0.f, 0.f);
         const float* qrow = s_q + tid * n;
@@ -366,8 +464,11 @@ static int launch_fk_l(const PathProgram& prog, const FkArgs& args, cudaStream_t
     const bool unrolled = prog.len <= 8 && (opt == 1 || (opt != 0 && (prog.n_dofs % 2) == 0));
     if (unrolled) return launch_fk<NDOF, TILE, WITH_JAC, 8>(prog, args, stream);
     // rolled walk: packed FP32x2 arithmetic (FFMA2) unless switched off for A/B measurements
-    return get_option(3) != 0 ? launch_fk<NDOF, TILE, WITH_JAC, -1>(prog, args, stream)
-                              : launch_fk<NDOF, TILE, WITH_JAC, 0>(prog, args, stream);
+    // fk_packed = 2: two configurations per thread in the two FP32x2 lanes (A/B candidate, see pair_walk)
+    const int packed = get_option(3);
+    if (packed == 2) return launch_fk<NDOF, TILE, WITH_JAC, -2>(prog, args, stream);
+    return packed != 0 ? launch_fk<NDOF, TILE, WITH_JAC, -1>(prog, args, stream)
+                       : launch_fk<NDOF, TILE, WITH_JAC, 0>(prog, args, stream);
 }
 template <int NDOF, int TILE>
 static int launch_fk_j(bool with_jac, const PathProgram& prog, const FkArgs& args, cudaStream_t stream) {

@@ -32,13 +32,15 @@ def main():
                torch.empty(big, 3, 7, device=DEV))
     stream = torch.cuda.Stream(device=DEV)
     rows = []
-    combos = [(1, 0, 1), (1, 0, 0), (1, 1, 1), (0, 0, 1)]      # (staging, unrolled, packed FP32x2); unrolled is always packed
+    combos = [(1, 0, 1), (1, 0, 2), (1, 0, 0), (1, 1, 1), (0, 0, 1)]   # (staging, unrolled, packed: 1 row pairs, 2 two configs/thread)
+    if os.environ.get("SWEEP_ONLY_PACKED"):
+        combos = [(1, 0, 1), (1, 0, 2)]
     for (variant, unroll, packed), tile in itertools.product(combos, (64, 128, 256)):
         engine.set_option("fk_variant", variant)
         engine.set_option("fk_unroll", unroll)
         engine.set_option("fk_packed", packed)
         engine.set_option("fk_tile", tile)
-        row = {"staging": "tma_bulk" if variant else "coop", "unrolled": bool(unroll), "packed_f32x2": bool(packed),
+        row = {"staging": "tma_bulk" if variant else "coop", "unrolled": bool(unroll), "packed_f32x2": int(packed),
                "tile": tile}
         with torch.cuda.stream(stream):
             # large batch

@@ -31,8 +31,9 @@ def cuda(a):
     return torch.tensor(np.asarray(a), dtype=torch.float32, device=DEV)
 
 
-@pytest.fixture(params=[(1, 0, 0, 1), (0, 0, 0, 1), (1, 1, 64, 1), (1, 0, 256, 0)],
-                ids=["tma_bulk_packed", "coop_copy_packed", "unrolled_tile64", "tile256_scalar"])
+@pytest.fixture(params=[(1, 0, 0, 1), (0, 0, 0, 1), (1, 1, 64, 1), (1, 0, 256, 0), (1, 0, 0, 2), (0, 0, 64, 2)],
+                ids=["tma_bulk_packed", "coop_copy_packed", "unrolled_tile64", "tile256_scalar", "two_configs_per_thread",
+                     "two_configs_coop_tile64"])
 def fk_variant(request):
     """Every staging / unrolling / tile / packed-arithmetic variant of the FK kernel must give the same parity."""
     variant, unroll, tile, packed = request.param
