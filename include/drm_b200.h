@@ -90,7 +90,8 @@ int64_t drmb200_launch_count(void);        /* kernels launched by this library s
  *   "fk_variant": 1 = TMA bulk-copy staging (default), 0 = cooperative float4 staging;
  *   "fk_tile":    configurations per CTA of the FK kernel, 64 / 128 / 256, 0 = chosen from the batch size (default);
  *   "fk_unroll":  0 = rolled chain walk, 1 = unrolled register-Jacobian kernel (paths <= 8 links), 2 = auto (default);
- *   "fk_packed":  1 = packed FP32x2 arithmetic (FFMA2) in the rolled chain walk (default), 0 = scalar FFMA;
+ *   "fk_packed":  1 = packed FP32x2 arithmetic (FFMA2) in the rolled chain walk (default), 0 = scalar FFMA,
+ *                 2 = two configurations per thread in the two FP32x2 lanes (measured slower; kept for A/B);
  *   "rnea_packed": 1 = packed FP32x2 arithmetic in the inverse-dynamics kernel (default), 0 = scalar FFMA. */
 int drmb200_set_option(const char* name, int value);
 
