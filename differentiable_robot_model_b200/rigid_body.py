@@ -28,6 +28,36 @@ class DifferentiableSpatialRigidBodyInertia(torch.nn.Module):
     def _get_parameter_values(self):
         return self.mass(), self.com(), self.inertia_mat()
 
+    # The two value-level operations of the reference class (``spatial_vector_algebra.py:321-372``), for callers that
+    # use the type directly.  The engine never calls them: the kernels read (I_o, m c, m) from the link table.
+    def _origin_inertia(self):
+        mass, com, inertia_mat = self._get_parameter_values()
+        mass = torch.as_tensor(mass).reshape(())
+        c = torch.as_tensor(com).reshape(3)
+        zero = torch.zeros((), dtype=c.dtype, device=c.device)
+        skew = torch.stack([torch.stack([zero, -c[2], c[1]]), torch.stack([c[2], zero, -c[0]]), torch.stack([-c[1], c[0], zero])])
+        return mass, mass * c, torch.as_tensor(inertia_mat).reshape(3, 3) + mass * (skew @ skew.t())
+
+    def multiply_motion_vec(self, smv):
+        """``I v`` for a spatial motion vector (``spatial_vector_algebra.py:321-338``): ``lin = m v.lin - (m c) x v.ang``,
+        ``ang = I_o v.ang + (m c) x v.lin`` with ``I_o = I_c + m S(c) S(c)^T`` (``inertia_mat`` used as given)."""
+        from .spatial_vector_algebra import SpatialForceVec
+        mass, mcom, inertia = self._origin_inertia()
+        mc = mcom.expand_as(smv.ang)
+        lin = mass * smv.lin - torch.linalg.cross(mc, smv.ang)
+        ang = smv.ang @ inertia.t() + torch.linalg.cross(mc, smv.lin)
+        return SpatialForceVec(lin, ang)
+
+    def get_spatial_mat(self):
+        """6x6 spatial inertia in [ang; lin] order, ``[[I_o, (m c)^], [((m c)^)^T, m 1]]`` (``:340-372``)."""
+        mass, mcom, inertia = self._origin_inertia()
+        zero = torch.zeros((), dtype=mcom.dtype, device=mcom.device)
+        skew = torch.stack([torch.stack([zero, -mcom[2], mcom[1]]), torch.stack([mcom[2], zero, -mcom[0]]),
+                            torch.stack([-mcom[1], mcom[0], zero])])
+        top = torch.cat([inertia, skew], dim=1)
+        bot = torch.cat([skew.t(), mass * torch.eye(3, dtype=mcom.dtype, device=mcom.device)], dim=1)
+        return torch.cat([top, bot], dim=0)
+
 
 class DifferentiableRigidBody(torch.nn.Module):
     """One link plus the joint that connects it to its parent (joint at the start of the link)."""

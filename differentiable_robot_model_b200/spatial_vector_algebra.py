@@ -183,3 +183,7 @@ class SpatialForceVec(_SpatialVec):
         lin = _apply(transform.rotation(), self.lin)
         ang = _apply(transform.trans_cross_rot(), self.lin) + _apply(transform.rotation(), self.ang)
         return SpatialForceVec(lin, ang)
+
+
+# the reference defines the inertia type in this module (spatial_vector_algebra.py:308); it lives next to the body here
+from .rigid_body import DifferentiableSpatialRigidBodyInertia  # noqa: E402,F401

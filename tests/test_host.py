@@ -183,3 +183,23 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert rc == -1 and b"ee_link" in lib.drmb200_last_error()
     rc = lib.drmb200_inverse_dynamics(ctypes.byref(topo), None, None, None, None, -5, 3, None, None)
     assert rc == -1
+
+
+def test_spatial_inertia_value_operations_match_the_oracle():
+    """DifferentiableSpatialRigidBodyInertia.multiply_motion_vec / get_spatial_mat (spatial_vector_algebra.py:321-372)
+    against the oracle's restatements (pinned to the reference through the dynamics golden vectors)."""
+    import differentiable_robot_model_b200 as drm
+    from differentiable_robot_model_b200.spatial_vector_algebra import (DifferentiableSpatialRigidBodyInertia,
+                                                                         SpatialMotionVec)
+    from oracle import drm_oracle as O
+    m = drm.DifferentiableKUKAiiwa()
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    gen = torch.Generator().manual_seed(0)
+    ang, lin = torch.randn(5, 3, generator=gen), torch.randn(5, 3, generator=gen)
+    for i in (1, 4, 7):
+        inertia = m._bodies[i].inertia
+        assert isinstance(inertia, DifferentiableSpatialRigidBodyInertia)
+        f = inertia.multiply_motion_vec(SpatialMotionVec(lin_motion=lin, ang_motion=ang))
+        o_lin, o_ang = O._inertia_times(robot, i, ang, lin)
+        assert torch.allclose(f.lin, o_lin, atol=1e-6) and torch.allclose(f.ang, o_ang, atol=1e-6)
+        assert torch.allclose(inertia.get_spatial_mat(), O._spatial_inertia(robot, i), atol=1e-7)
