@@ -91,6 +91,32 @@ class DifferentiableRigidBody(torch.nn.Module):
         self._ctor_trans = rigid_body_params["trans"].reshape(1, 3).detach().clone()
         self._ctor_rot_angles = rigid_body_params["rot_angles"].reshape(1, 3).detach().clone()
 
+    # Per-joint value helpers with the reference's names and semantics (rigid_body.py:130-165): joint pose
+    # R_fix(rpy) R_axis(sign q) / trans, joint velocity and acceleration about the signed axis.  The model's compute_*
+    # entry points never call them (the kernels do this per link in registers); they exist for callers that walk the
+    # bodies themselves.
+    def update_joint_state(self, q, qd):
+        from .spatial_vector_algebra import CoordinateTransform, SpatialMotionVec, x_rot, y_rot, z_rot
+        batch = q.shape[0]
+        axis = self.joint_axis.reshape(1, 3).to(q.device)
+        ang_vel = qd.reshape(batch, 1) @ axis
+        self.joint_vel = SpatialMotionVec(torch.zeros_like(ang_vel), ang_vel)
+        rpy = self.rot_angles().reshape(3).to(q.device)
+        fixed = (z_rot(rpy[2]) @ y_rot(rpy[1])) @ x_rot(rpy[0])
+        if torch.abs(axis[0, 0]) == 1:
+            rot = x_rot(torch.sign(axis[0, 0]) * q)
+        elif torch.abs(axis[0, 1]) == 1:
+            rot = y_rot(torch.sign(axis[0, 1]) * q)
+        else:
+            rot = z_rot(torch.sign(axis[0, 2]) * q)
+        self.joint_pose = CoordinateTransform(rot=fixed.expand(batch, 3, 3) @ rot,
+                                              trans=self.trans().reshape(1, 3).to(q.device).expand(batch, 3), device=q.device)
+
+    def update_joint_acc(self, qdd):
+        from .spatial_vector_algebra import SpatialMotionVec
+        ang_acc = qdd.reshape(qdd.shape[0], 1) @ self.joint_axis.reshape(1, 3).to(qdd.device)
+        self.joint_acc = SpatialMotionVec(torch.zeros_like(ang_acc), ang_acc)
+
     # kinematic tree construction (robot_model.py:133-137)
     def set_parent(self, link: "DifferentiableRigidBody"):
         object.__setattr__(self, "_parent", link)

@@ -203,3 +203,24 @@ def test_spatial_inertia_value_operations_match_the_oracle():
         o_lin, o_ang = O._inertia_times(robot, i, ang, lin)
         assert torch.allclose(f.lin, o_lin, atol=1e-6) and torch.allclose(f.ang, o_ang, atol=1e-6)
         assert torch.allclose(inertia.get_spatial_mat(), O._spatial_inertia(robot, i), atol=1e-7)
+
+
+def test_per_joint_value_helpers_match_the_oracle():
+    """DifferentiableRigidBody.update_joint_state / update_joint_acc (rigid_body.py:130-165) against the oracle's
+    joint_transform for every movable Kuka joint."""
+    import differentiable_robot_model_b200 as drm
+    from oracle import drm_oracle as O
+    m = drm.DifferentiableKUKAiiwa()
+    robot = O.load_robot(m.urdf_path, torch.float32)
+    q, qd, qdd = O.sample_inputs(robot, 6, seed=2)
+    for i, body in enumerate(m._bodies):
+        if body.joint_idx is None:
+            continue
+        k = body.joint_idx
+        body.update_joint_state(q[:, k:k + 1], qd[:, k:k + 1])
+        body.update_joint_acc(qdd[:, k:k + 1])
+        Rj, tj = O.joint_transform(robot, i, q)
+        assert torch.allclose(body.joint_pose.rotation(), Rj, atol=1e-6)
+        assert torch.allclose(body.joint_pose.translation(), tj.expand(6, 3), atol=1e-7)
+        assert torch.allclose(body.joint_vel.ang, qd[:, k:k + 1] @ robot.axis[i:i + 1]) and float(body.joint_vel.lin.abs().max()) == 0
+        assert torch.allclose(body.joint_acc.ang, qdd[:, k:k + 1] @ robot.axis[i:i + 1])
