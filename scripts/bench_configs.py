@@ -90,8 +90,29 @@ def bench_rnea(stem_cls, batch):
     ms = timed(lambda i: engine.inverse_dynamics_raw(topo, table, *sets[i % len(sets)], 3, out=outs[i % len(sets)]),
                200 if batch <= (1 << 17) else 20)
     by = 16 * n
-    return {"batch": batch, "ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
-            "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK}
+    res = {"batch": batch, "ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
+           "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK}
+    if batch <= 65536 and engine.lib().drmb200_set_option is not None and os.environ.get("DRMB200_SKIP_CPU") is None:
+        # CPU beside it, same box: scalar C port on all cores and the torch port (bounded samples)
+        import time
+        from oracle.c_oracle import CRobot
+        cr = CRobot(robot)
+        nq, nqd, nqdd = (t.cpu().numpy() for t in sets[0])
+        cr.inverse_dynamics(nq[:4096], nqd[:4096], nqdd[:4096])
+        t0 = time.perf_counter()
+        cr.inverse_dynamics(nq, nqd, nqdd)
+        res["cpu_c_port_configs_per_s"] = batch / (time.perf_counter() - t0)
+        res["cpu_c_port_cores"] = os.cpu_count()
+        cq = [t[:4096].cpu() for t in sets[0]]
+        torch.set_num_threads(8)
+        with torch.no_grad():
+            O.inverse_dynamics(robot, *cq)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                O.inverse_dynamics(robot, *cq)
+        res["cpu_torch_port_configs_per_s"] = 3 * 4096 / (time.perf_counter() - t0)
+        res["cpu_torch_port_threads"] = 8
+    return res
 
 
 def bench_forward_dynamics(stem_cls, batch):
