@@ -224,3 +224,21 @@ def test_per_joint_value_helpers_match_the_oracle():
         assert torch.allclose(body.joint_pose.translation(), tj.expand(6, 3), atol=1e-7)
         assert torch.allclose(body.joint_vel.ang, qd[:, k:k + 1] @ robot.axis[i:i + 1]) and float(body.joint_vel.lin.abs().max()) == 0
         assert torch.allclose(body.joint_acc.ang, qdd[:, k:k + 1] @ robot.axis[i:i + 1])
+
+
+def test_table_staging_permutation_matches_its_definition(tmp_path):
+    """The select-based row permutation the kernels stage the link table with (canonical_row, csrc/drm_common.cuh)
+    against the element-wise definition canon_map(), all 49 (parent axis, link axis) code pairs -- compiled for the
+    host with nvcc and run on the CPU."""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "canon_check")
+    subprocess.run([nvcc, "-std=c++17", "-arch=sm_100a", "-I", os.path.join(repo, "differentiable_robot_model_b200", "csrc"),
+                    "-o", exe, os.path.join(repo, "tests", "host_checks", "canon_check.cu")], check=True, capture_output=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    assert "all 49" in out.stdout
