@@ -1,43 +1,39 @@
-"""Learn the two joint origins of the planar 2-link toy robot from end-effector positions, freezing and
-un-freezing one of them on the way (B200 engine).
+"""Recover both joint origins of the planar 2-link toy robot from end-effector positions, freezing one of them for a
+while on the way (B200 engine).
 
-Same experiment as the reference's ``examples/learn_kinematics_of_toy.py:27`` -- ``run(n_epochs, n_data, device)``.
-Every ``compute_forward_kinematics`` call is one kernel launch; ``loss.backward()`` runs the analytic adjoint.
+The experiment of the reference's ``examples/learn_kinematics_of_toy.py`` (``run(n_epochs, n_data, device)``, :27),
+including its freeze at iteration 10 / unfreeze at iteration 100.
 """
 import torch
 
+from common import fit_full_batch
 from differentiable_robot_model_b200 import DifferentiableRobotModel, DifferentiableTwoLinkRobot
 from differentiable_robot_model_b200.data_utils import generate_random_forward_kinematics_data
 from differentiable_robot_model_b200.rigid_body_params import UnconstrainedTensor
 
+EE = "endEffector"
+
 
 def run(n_epochs=3000, n_data=100, device="cuda"):
-    gt_robot_model = DifferentiableTwoLinkRobot(device=device)
-    learnable_robot_model = DifferentiableRobotModel(gt_robot_model.urdf_path, name="2link", device=device)
-    learnable_robot_model.make_link_param_learnable("arm1", "trans", UnconstrainedTensor(dim1=1, dim2=3))
-    learnable_robot_model.make_link_param_learnable("arm2", "trans", UnconstrainedTensor(dim1=1, dim2=3))
+    truth = DifferentiableTwoLinkRobot(device=device)
+    student = DifferentiableRobotModel(truth.urdf_path, name="2link", device=device)
+    for link in ("arm1", "arm2"):
+        student.make_link_param_learnable(link, "trans", UnconstrainedTensor(dim1=1, dim2=3))
+    samples = generate_random_forward_kinematics_data(truth, n_data=n_data, ee_name=EE)
 
-    train_data = generate_random_forward_kinematics_data(gt_robot_model, n_data=n_data, ee_name="endEffector")
-    q, gt_ee_pos = train_data["q"], train_data["ee_pos"]
+    def position_error():
+        predicted, _ = student.compute_forward_kinematics(q=samples["q"], link_name=EE)
+        return torch.nn.functional.mse_loss(predicted, samples["ee_pos"])
 
-    optimizer = torch.optim.Adam(learnable_robot_model.parameters(), lr=1e-3)
-    loss_fn = torch.nn.MSELoss()
-    history = []
-    for i in range(n_epochs):
-        optimizer.zero_grad()
-        ee_pos_pred, _ = learnable_robot_model.compute_forward_kinematics(q=q, link_name="endEffector")
-        loss = loss_fn(ee_pos_pred, gt_ee_pos)
-        history.append(float(loss.detach()))
-        if i % 500 == 0:
-            print(f"i: {i}, loss: {history[-1]}")
+    def schedule(i):
         if i == 10:
-            learnable_robot_model.freeze_learnable_link_param(link_name="arm1", parameter_name="trans")
-        if i == 100:
-            learnable_robot_model.unfreeze_learnable_link_param(link_name="arm1", parameter_name="trans")
-        loss.backward()
-        optimizer.step()
-    print("ground-truth joint origins:", gt_robot_model._bodies[1].trans(), gt_robot_model._bodies[2].trans())
-    learnable_robot_model.print_learnable_params()
+            student.freeze_learnable_link_param(link_name="arm1", parameter_name="trans")
+        elif i == 100:
+            student.unfreeze_learnable_link_param(link_name="arm1", parameter_name="trans")
+
+    history = fit_full_batch(student.parameters(), position_error, n_epochs, every=500, before_step=schedule)
+    print("ground-truth joint origins:", truth._bodies[1].trans(), truth._bodies[2].trans())
+    student.print_learnable_params()
     return history
 
 
