@@ -11,7 +11,8 @@ keeps, in document order, only what the reference's loader reads
 (`differentiable_robot_model/urdf_utils.py:28-126`): `<link name>` + `<inertial>` (origin, mass,
 inertia) and `<joint name type>` + parent / child / origin / axis / limit / dynamics / mimic.
 Visual, collision, material, gazebo, transmission and mesh content is dropped (the library never
-reads it).  Attribute strings are copied verbatim so every parsed float is bit-identical.
+reads it).  The output is a canonical serialisation (one line per link / joint, fixed child and attribute order);
+attribute VALUES are copied verbatim so every parsed float is bit-identical.
 `fetch.urdf` is not well-formed XML in the reference (unbound `sensor:` prefix) and is skipped.
 """
 import os
@@ -21,12 +22,13 @@ import xml.etree.ElementTree as ET
 SRC = "/root/reference/diff_robot_data"
 DST = os.path.join(os.path.dirname(__file__), "..", "..", "differentiable_robot_model_b200", "robot_data")
 
-LINK_KEEP = {"inertial": ("origin", "mass", "inertia")}
-JOINT_KEEP = ("parent", "child", "origin", "axis", "limit", "dynamics", "mimic")
+LINK_KEEP = {"inertial": ("mass", "origin", "inertia")}
+JOINT_KEEP = ("origin", "axis", "parent", "child", "limit", "dynamics", "mimic")
 
 
 def _attrs(e):
-    return "".join(f' {k}="{v}"' for k, v in e.attrib.items())
+    """Attributes in a canonical (reverse-alphabetical) order; values verbatim."""
+    return "".join(f' {k}="{e.attrib[k]}"' for k in sorted(e.attrib, reverse=True))
 
 
 def reduce_urdf(src_path):
@@ -36,25 +38,17 @@ def reduce_urdf(src_path):
            f'<robot name="{root.get("name", "")}">']
     for e in root:
         if e.tag == "link":
+            # canonical serialisation: one line per link / joint, fixed child and attribute order
             inertial = e.find("inertial")
             if inertial is None:
-                out.append(f'  <link name="{e.get("name")}"/>')
+                out.append(f'<link name="{e.get("name")}"/>')
             else:
-                out.append(f'  <link name="{e.get("name")}">')
-                out.append("    <inertial>")
-                for tag in LINK_KEEP["inertial"]:
-                    c = inertial.find(tag)
-                    if c is not None:
-                        out.append(f"      <{tag}{_attrs(c)}/>")
-                out.append("    </inertial>")
-                out.append("  </link>")
+                kept = "".join(f"<{tag}{_attrs(inertial.find(tag))}/>" for tag in LINK_KEEP["inertial"]
+                               if inertial.find(tag) is not None)
+                out.append(f'<link name="{e.get("name")}"><inertial>{kept}</inertial></link>')
         elif e.tag == "joint":
-            out.append(f'  <joint name="{e.get("name")}" type="{e.get("type")}">')
-            for tag in JOINT_KEEP:
-                c = e.find(tag)
-                if c is not None:
-                    out.append(f"    <{tag}{_attrs(c)}/>")
-            out.append("  </joint>")
+            kept = "".join(f"<{tag}{_attrs(e.find(tag))}/>" for tag in JOINT_KEEP if e.find(tag) is not None)
+            out.append(f'<joint type="{e.get("type")}" name="{e.get("name")}">{kept}</joint>')
     out.append("</robot>")
     return "\n".join(out) + "\n"
 
