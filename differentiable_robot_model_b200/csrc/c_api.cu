@@ -14,7 +14,28 @@ namespace drm {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
-static std::atomic<int> g_options[6] = {{-1}, {-1}, {-1}, {-1}, {-1}, {-1}};   // 0: fk_variant, 1: fk_tile, 2: fk_unroll, 3: fk_packed, 4: rnea_packed, 5: host_fused
+// Tuning knobs for A/B measurements, overridable with the environment (DRMB200_<NAME IN CAPITALS>) or drmb200_set_option().
+struct Option { const char* name; const char* env; int def; };
+static const Option g_option_table[] = {
+    {"fk_variant", "DRMB200_FK_VARIANT", 1},     // 0: staging: 1 = TMA bulk copies (default), 0 = cooperative float4 copies
+    {"fk_tile", "DRMB200_FK_TILE", 0},           // 1: CTA-tile kernel: configurations per CTA, 64 / 128 / 256; 0 = by batch size
+    {"fk_unroll", "DRMB200_FK_UNROLL", 2},       // 2: 0 rolled walk, 1 unrolled register-Jacobian kernel (paths <= 8 links),
+                                                 //    2 = auto: unrolled only for even n_dofs (profiles/r01/v3_sweep_fk_variants.json)
+    {"fk_packed", "DRMB200_FK_PACKED", 1},       // 3: 1 packed FP32x2 arithmetic (default), 0 scalar, 2 two configurations per thread
+    {"rnea_packed", "DRMB200_RNEA_PACKED", 1},   // 4: packed FP32x2 arithmetic in the RNEA kernel
+    {"host_fused", "DRMB200_HOST_FUSED", 1},     // 5: drmb200_fk_jacobian_host on page-locked buffers: 1 = one launch whose TMA
+                                                 //    copies cross PCIe themselves (default), 0 = staged H2D -> kernel -> D2H
+    {"fk_reserved", "DRMB200_FK_RESERVED", 0},   // 6: unused (was the per-warp pipeline kernel A/B, profiles/r02/v13_lab_fk_launch_per_warp_kernel.json)
+    {"fk_pdl", "DRMB200_FK_PDL", 0},             // 7: programmatic dependent launch of the FK kernels: 0 off (default);
+                                                 //    2 = a launch may run ahead of the FK launches before it on the stream up
+                                                 //    to its first global write (the library falls back to an ordinary launch when
+                                                 //    an input overlaps an output of the launches still in flight, see
+                                                 //    pdl_mode_for_launch in fk_jacobian.cu); 1 = wait before the first global
+                                                 //    read (A/B only: measured slower than 0)
+};
+constexpr int N_OPTIONS = sizeof(g_option_table) / sizeof(g_option_table[0]);
+static std::atomic<int> g_options[N_OPTIONS];
+static std::atomic<int> g_options_set[N_OPTIONS];
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -24,30 +45,23 @@ void set_error(const char* fmt, ...) {
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-// Tuning knobs for A/B measurements, overridable with the environment or drmb200_set_option():
-//   0 "fk_variant" (DRMB200_FK_VARIANT): 1 = TMA bulk-copy staging (default), 0 = cooperative float4 copies
-//   1 "fk_tile"    (DRMB200_FK_TILE):    configurations per CTA, 64 / 128 / 256; 0 = pick by batch size
-//   2 "fk_unroll"  (DRMB200_FK_UNROLL):  0 = rolled chain walk, 1 = fully unrolled register-Jacobian kernel for
-//                  paths <= 8 links, 2 = auto (default): unrolled only for even n_dofs.  Measured
-//                  (profiles/r01/v3_sweep_fk_variants.json, v5_bench_other_configs.json): for the 7-DoF Kuka the
-//                  unrolled variant (80 registers, ~3x the code) is SLOWER (16.8 vs 20.6 G cfg/s at 65 536 x 4 in
-//                  flight, 19.8 vs 21.0 at 2^22); for the 16-DoF Allegro hand, whose even row strides make every J-tile
-//                  access a 16-way bank conflict, touching the tile once per column wins (9.8 vs 6.3 G cfg/s).
-//   3 "fk_packed"  (DRMB200_FK_PACKED):  1 = packed FP32x2 (FFMA2) arithmetic in the rolled chain walk (default), 0 = scalar
-//   4 "rnea_packed" (DRMB200_RNEA_PACKED): 1 = packed FP32x2 arithmetic in the RNEA kernel (default), 0 = scalar
-//   5 "host_fused" (DRMB200_HOST_FUSED): drmb200_fk_jacobian_host with page-locked buffers: 1 = one launch whose TMA copies
-//                  read / write host memory directly (default), 0 = staged H2D -> kernel -> D2H pipeline
 int get_option(int which) {
-    int v = g_options[which].load(std::memory_order_relaxed);
-    if (v < 0) {
-        static const char* names[6] = {"DRMB200_FK_VARIANT", "DRMB200_FK_TILE", "DRMB200_FK_UNROLL", "DRMB200_FK_PACKED",
-                                       "DRMB200_RNEA_PACKED", "DRMB200_HOST_FUSED"};
-        static const int defaults[6] = {1, 0, 2, 1, 1, 1};
-        const char* e = getenv(names[which]);
-        v = e ? atoi(e) : defaults[which];
-        g_options[which].store(v, std::memory_order_relaxed);
+    if (!g_options_set[which].load(std::memory_order_acquire)) {
+        const char* e = getenv(g_option_table[which].env);
+        g_options[which].store(e ? atoi(e) : g_option_table[which].def, std::memory_order_relaxed);
+        g_options_set[which].store(1, std::memory_order_release);
     }
-    return v;
+    return g_options[which].load(std::memory_order_relaxed);
+}
+static int set_option_by_name(const char* name, int value) {
+    if (name == nullptr) return DRMB200_EINVAL;
+    for (int i = 0; i < N_OPTIONS; ++i)
+        if (std::string(name) == g_option_table[i].name) {
+            g_options[i].store(value, std::memory_order_relaxed);
+            g_options_set[i].store(1, std::memory_order_release);
+            return DRMB200_OK;
+        }
+    return DRMB200_EINVAL;
 }
 
 // implemented in the kernel translation units
@@ -206,12 +220,7 @@ int64_t drmb200_launch_count(void) { return drm::g_launches.load(); }
 
 // not part of the reference-facing surface: A/B switch used by bench.py and the tests
 int drmb200_set_option(const char* name, int value) {
-    if (name != nullptr && std::string(name) == "fk_variant") { drm::g_options[0].store(value); return DRMB200_OK; }
-    if (name != nullptr && std::string(name) == "fk_tile") { drm::g_options[1].store(value); return DRMB200_OK; }
-    if (name != nullptr && std::string(name) == "fk_unroll") { drm::g_options[2].store(value); return DRMB200_OK; }
-    if (name != nullptr && std::string(name) == "fk_packed") { drm::g_options[3].store(value); return DRMB200_OK; }
-    if (name != nullptr && std::string(name) == "rnea_packed") { drm::g_options[4].store(value); return DRMB200_OK; }
-    if (name != nullptr && std::string(name) == "host_fused") { drm::g_options[5].store(value); return DRMB200_OK; }
+    if (drm::set_option_by_name(name, value) == DRMB200_OK) return DRMB200_OK;
     drm::set_error("unknown option");
     return DRMB200_EINVAL;
 }

@@ -26,6 +26,7 @@
 //
 // Algorithmic HBM bytes per configuration: 4n (q) + 12 (pos) + 16 (quat) + 24n (J) = 28n + 28
 // (224 B for the 7-DoF Kuka iiwa) -- SURVEY.md section 8(d).
+#include <mutex>
 #include "drm_common.cuh"
 
 namespace drm {
@@ -40,7 +41,13 @@ struct FkArgs {
     int64_t batch;
     int32_t aligned;                     // all base pointers 16-byte aligned
     int32_t use_bulk;                    // staging variant: 1 TMA bulk copies, 0 cooperative copies
+    int32_t pdl;                         // programmatic dependent launch (per-warp kernel): 0 off, 1 wait before the first
+                                         // global read, 2 wait before the first global write (caller-asserted independence)
 };
+
+// Programmatic dependent launch (PTX griddepcontrol): release the next launch on the stream / wait for the previous grid
+__device__ __forceinline__ void grid_dep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // shared-memory carve-up (floats), natural global layout per region
 struct FkSmemLayout {
@@ -83,6 +90,55 @@ __device__ __forceinline__ void walk_link(const float* row, const float* qrow, i
             m = cross(z, v3(px, py, p2));
         }
         rotate_z_p(R, cs, sn);
+    }
+}
+
+// Rolled chain walk with packed FP32x2 arithmetic (FFMA2 / FMUL2): rows 0,1 of R and (p.x, p.y) live in 64-bit register
+// pairs; 35 instead of 54 arithmetic instructions per movable link, same operations in the same order as the scalar walk.
+// Explicit shared-window addresses (see smem_addr_opaque): table cursor a_tab, this thread's q row a_q and J rows a_jl / a_ja
+// (n4 = 4 n_dofs bytes).  Each path joint parks z_i (its final J_ang column) and z_i x p_i in the thread's rows of the J tile.
+template <bool WITH_JAC>
+__device__ __forceinline__ void walk_rolled_packed(const PathProgram& prog, int len, uint32_t a_tab, uint32_t a_q,
+                                                   uint32_t a_jl, uint32_t a_ja, uint32_t n4, M3& R, V3& p) {
+    M3P Rp = identity3p();
+    f32x2 pp = pk2(0.f, 0.f);
+    float p2 = 0.f;
+    for (int k = 0; k < len; ++k, a_tab += 48) {
+        M3 F; V3 r;
+        load_Fr_s(a_tab, F, r);
+        mul_add_p(Rp, r, pp, p2);
+        Rp = mul_p(Rp, F);
+        const int c = prog.dof[k];
+        if (c >= 0) {
+            float sn, cs;
+            sincos_pi2(lds_f32(a_q + 4u * c), sn, cs);
+            if (WITH_JAC) {
+                float zx, zy, px, py;
+                upk2(Rp.c2, zx, zy);
+                upk2(pp, px, py);
+                const V3 z = v3(zx, zy, Rp.a22);
+                const V3 m = cross(z, v3(px, py, p2));
+                const uint32_t o = 4u * c;
+                sts_f32(a_ja + o, z.x); sts_f32(a_ja + o + n4, z.y); sts_f32(a_ja + o + 2 * n4, z.z);
+                sts_f32(a_jl + o, m.x); sts_f32(a_jl + o + n4, m.y); sts_f32(a_jl + o + 2 * n4, m.z);
+            }
+            rotate_z_p(Rp, cs, sn);
+        }
+    }
+    R = unpack3(Rp);
+    upk2(pp, p.x, p.y);
+    p.z = p2;
+}
+// Second pass: J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
+__device__ __forceinline__ void jlin_fixup(const PathProgram& prog, int len, uint32_t a_jl, uint32_t a_ja, uint32_t n4, V3 p) {
+    for (int k = 0; k < len; ++k) {
+        const int c = prog.dof[k];
+        if (c < 0) continue;
+        const uint32_t o = 4u * c;
+        const V3 z = v3(lds_f32(a_ja + o), lds_f32(a_ja + o + n4), lds_f32(a_ja + o + 2 * n4));
+        const V3 m = v3(lds_f32(a_jl + o), lds_f32(a_jl + o + n4), lds_f32(a_jl + o + 2 * n4));
+        const V3 j = cross_add(z, p, v3(-m.x, -m.y, -m.z));
+        sts_f32(a_jl + o, j.x); sts_f32(a_jl + o + n4, j.y); sts_f32(a_jl + o + 2 * n4, j.z);
     }
 }
 
@@ -205,6 +261,11 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
     const bool bulk = args.use_bulk && args.aligned && ((valid & 3) == 0);
     const bool vec_ok = args.aligned;   // base pointers 16-byte aligned; tile offsets always are
 
+    // Programmatic dependent launch (see "fk_pdl" in drm_b200.h): the next launch on the stream may start now; this grid
+    // waits for its predecessor before its first global read (pdl 1) or only before its first global write (pdl 2)
+    if (args.pdl) grid_dep_launch_dependents();
+    if (args.pdl == 1) grid_dep_wait();
+
     // ---- stage inputs --------------------------------------------------------------------------
     if (bulk) {
         if (tid == 0) {
@@ -282,36 +343,7 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
             const uint32_t a_jl = smem_addr_opaque(jl), a_ja = smem_addr_opaque(ja);
             const uint32_t n4 = 4u * n;
             if (MAXLEN < 0) {
-                // packed FP32x2 walk (FFMA2 / FMUL2): rows 0,1 of R and (p.x, p.y) live in 64-bit register pairs;
-                // 35 instead of 54 arithmetic instructions per movable link, same operations in the same order
-                M3P Rp = identity3p();
-                f32x2 pp = pk2(0.f, 0.f);
-                float p2 = 0.f;
-                for (int k = 0; k < len; ++k, a_tab += 48) {
-                    M3 F; V3 r;
-                    load_Fr_s(a_tab, F, r);
-                    mul_add_p(Rp, r, pp, p2);
-                    Rp = mul_p(Rp, F);
-                    const int c = prog.dof[k];
-                    if (c >= 0) {
-                        float sn, cs;
-                        sincos_pi2(lds_f32(a_q + 4u * c), sn, cs);
-                        if (WITH_JAC) {
-                            float zx, zy, px, py;
-                            upk2(Rp.c2, zx, zy);
-                            upk2(pp, px, py);
-                            const V3 z = v3(zx, zy, Rp.a22);
-                            const V3 m = cross(z, v3(px, py, p2));
-                            const uint32_t o = 4u * c;
-                            sts_f32(a_ja + o, z.x); sts_f32(a_ja + o + n4, z.y); sts_f32(a_ja + o + 2 * n4, z.z);
-                            sts_f32(a_jl + o, m.x); sts_f32(a_jl + o + n4, m.y); sts_f32(a_jl + o + 2 * n4, m.z);
-                        }
-                        rotate_z_p(Rp, cs, sn);
-                    }
-                }
-                R = unpack3(Rp);
-                upk2(pp, p.x, p.y);
-                p.z = p2;
+                walk_rolled_packed<WITH_JAC>(prog, len, a_tab, a_q, a_jl, a_ja, n4, R, p);
             } else {
             for (int k = 0; k < len; ++k, a_tab += 48) {
                 M3 F; V3 r;
@@ -333,18 +365,7 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
                 }
             }
             }
-            if (WITH_JAC) {
-                // J_lin[:,c] = z x (p_ee - p_i) = z x p_ee - z x p_i      (robot_model.py:661)
-                for (int k = 0; k < len; ++k) {
-                    const int c = prog.dof[k];
-                    if (c < 0) continue;
-                    const uint32_t o = 4u * c;
-                    const V3 z = v3(lds_f32(a_ja + o), lds_f32(a_ja + o + n4), lds_f32(a_ja + o + 2 * n4));
-                    const V3 m = v3(lds_f32(a_jl + o), lds_f32(a_jl + o + n4), lds_f32(a_jl + o + 2 * n4));
-                    const V3 j = cross_add(z, p, v3(-m.x, -m.y, -m.z));
-                    sts_f32(a_jl + o, j.x); sts_f32(a_jl + o + n4, j.y); sts_f32(a_jl + o + 2 * n4, j.z);
-                }
-            }
+            if (WITH_JAC) jlin_fixup(prog, len, a_jl, a_ja, n4, p);
         }
 
         if (args.pos != nullptr) { s_pos[tid * 3 + 0] = p.x; s_pos[tid * 3 + 1] = p.y; s_pos[tid * 3 + 2] = p.z; }
@@ -359,6 +380,7 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
         fence_proxy_async();                 // generic-proxy smem writes -> visible to the async proxy
         __syncthreads();
         if (tid == 0) {
+            if (args.pdl == 2) grid_dep_wait();
             if (args.pos != nullptr) bulk_s2g(args.pos + tile_start * 3, s_pos, (uint32_t)valid * 12u);
             if (args.quat != nullptr) bulk_s2g(args.quat + tile_start * 4, s_quat, (uint32_t)valid * 16u);
             if (WITH_JAC) {
@@ -370,6 +392,7 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
         }
     } else {
         __syncthreads();
+        if (args.pdl == 2) grid_dep_wait();
         if (args.pos != nullptr) coop_copy(args.pos + tile_start * 3, s_pos, valid * 3, vec_ok);
         if (args.quat != nullptr) coop_copy(args.quat + tile_start * 4, s_quat, valid * 4, vec_ok);
         if (WITH_JAC) {
@@ -448,8 +471,17 @@ static int launch_fk(const PathProgram& prog, const FkArgs& args, cudaStream_t s
     }
     const int64_t tiles = (args.batch + TILE - 1) / TILE;
     if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
-    kern<<<(unsigned)tiles, TILE, smem_bytes, stream>>>(prog, args);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3(TILE);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = args.pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prog, args);
     if (e != cudaSuccess) { set_error("fk_jacobian launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
     return DRMB200_OK;
@@ -481,6 +513,55 @@ static int launch_fk_t(int tile, bool with_jac, const PathProgram& prog, const F
     return launch_fk_j<NDOF, 128>(with_jac, prog, args, stream);
 }
 
+// ---- programmatic dependent launch: which mode is safe for THIS launch -------------------------------------------
+// "fk_pdl" 2 lets a launch run ahead of its predecessors on the stream up to its first global WRITE.  Only FK launches
+// release their dependents early, so the only stream-order hazard is a launch READING (q, table) what one of the FK
+// launches still in flight ahead of it writes.  How many can be in flight: a launch starts only when every CTA of its
+// predecessor has started, and a started CTA keeps its shared memory until its own predecessor grid has completed, so the
+// grids ahead of a launch that are not yet complete are all fully resident -- at most 1 / f of them, f = the share of the
+// GPU's shared memory one grid takes.  The library therefore (a) uses mode 2 only for launches with f >= 1/4 and (b) keeps
+// the output ranges of the last 8 FK launches per (device, stream) and falls back to an ordinary launch whenever an input
+// of the new launch overlaps one of them.  Writes need no check: every launch waits for its predecessor before writing.
+struct Range { uintptr_t lo, hi; };
+struct StreamLog { int dev; cudaStream_t stream; bool used; int head; Range out[8][4]; };
+static StreamLog g_logs[16];
+static std::mutex g_log_mu;
+static int g_log_clock = 0;
+
+static bool overlaps(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
+
+static int pdl_mode_for_launch(const PathProgram& prog, const FkArgs& args, int n_links, cudaStream_t stream) {
+    int mode = get_option(7);
+    if (mode < 0 || mode > 2) mode = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int n = prog.n_dofs;
+    const uintptr_t B = (uintptr_t)args.batch;
+    auto range = [](const void* p, uintptr_t bytes) { Range r; r.lo = (uintptr_t)p; r.hi = p ? (uintptr_t)p + bytes : 0; return r; };
+    const Range outs[4] = {range(args.pos, B * 12), range(args.quat, B * 16), range(args.jlin, B * 12 * n), range(args.jang, B * 12 * n)};
+    const Range ins[2] = {range(args.q, B * 4 * n), range(args.table, (uintptr_t)n_links * DRMB200_TABLE_STRIDE * 4)};
+    std::lock_guard<std::mutex> lock(g_log_mu);
+    StreamLog* log = nullptr;
+    for (auto& l : g_logs) if (l.used && l.dev == dev && l.stream == stream) { log = &l; break; }
+    if (log == nullptr) {                                   // claim a slot (round robin; a recycled slot starts empty)
+        log = &g_logs[g_log_clock++ & 15];
+        *log = StreamLog();
+        log->used = true; log->dev = dev; log->stream = stream;
+    }
+    if (mode == 2) {
+        // share of the GPU's shared memory this grid takes (the residency bound above)
+        const double smem_per_config = 4.0 * (n + 7 + (args.jlin ? 6 * n : 0));
+        const double f = smem_per_config * (double)args.batch / (148.0 * 227.0 * 1024.0);
+        if (f < 0.25) mode = 0;
+        for (int k = 0; k < 8 && mode == 2; ++k)
+            for (int o = 0; o < 4 && mode == 2; ++o)
+                if (overlaps(log->out[k][o], ins[0]) || overlaps(log->out[k][o], ins[1])) mode = 0;
+    }
+    for (int o = 0; o < 4; ++o) log->out[log->head][o] = outs[o];
+    log->head = (log->head + 1) & 7;
+    return mode;
+}
+
 int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const float* table, const float* q,
                        int64_t batch, float* pos, float* quat, float* jlin, float* jang, cudaStream_t stream) {
     PathProgram prog;
@@ -498,6 +579,9 @@ int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const fl
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.aligned = (al16(q) && al16(pos) && al16(quat) && al16(jlin) && al16(jang)) ? 1 : 0;
     args.use_bulk = get_option(0) != 0;
+    const bool with_jac = jlin != nullptr;
+    args.pdl = pdl_mode_for_launch(prog, args, topo->n_links, stream);
+
 
     // Tile size, from the measured sweep (profiles/r01/v3_sweep_fk_variants.json, Kuka, rolled kernel):
     //   2^22 per launch:   tile 64 -> 21.99 G cfg/s, 128 -> 20.96, 256 -> 16.66   (shared memory, 32 n + 28 bytes
@@ -506,8 +590,10 @@ int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const fl
     int tile = get_option(1);
     //   16-DoF Allegro hand, 2^21 per launch: tile 128 -> 9.8 G cfg/s, tile 64 -> 7.0 (even row strides: 16-way
     //                      bank conflicts hurt the narrower tile more), so wide rows keep 128
-    if (tile != 64 && tile != 128 && tile != 256) tile = (batch <= 148 * 1024 || prog.n_dofs > 8) ? 128 : 64;
-    const bool with_jac = jlin != nullptr;
+    //   with programmatic dependent launch (fk_pdl 2) consecutive launches overlap and the sub-wave ramp no longer
+    //   matters: tile 64 -> 2.85 us per stream-ordered 65 536 launch, tile 128 -> 3.41 us (profiles/r02/v13_lab_fk_launch_pdl.json)
+    if (tile != 64 && tile != 128 && tile != 256)
+        tile = (prog.n_dofs > 8 || (batch <= 148 * 1024 && args.pdl != 2)) ? 128 : 64;
     switch (prog.n_dofs) {
         case 2: return launch_fk_t<2>(tile, with_jac, prog, args, stream);
         case 7: return launch_fk_t<7>(tile, with_jac, prog, args, stream);

@@ -36,6 +36,22 @@ def pytest_configure(config):
     torch.set_num_threads(min(8, os.cpu_count() or 1))
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests need a CUDA device and the built C-ABI library: skip (not fail) where either is missing."""
+    import torch
+    from differentiable_robot_model_b200 import engine
+    reason = None
+    if not torch.cuda.is_available():
+        reason = "needs a CUDA device"
+    elif not os.path.exists(engine.library_path()):
+        reason = f"{engine.library_path()} has not been built"
+    if reason:
+        skip = pytest.mark.skip(reason=reason)
+        for item in items:
+            if "gpu" in item.keywords:
+                item.add_marker(skip)
+
+
 def urdf_path(stem):
     return os.path.join(ROBOT_DATA, URDFS[stem])
 
