@@ -535,7 +535,7 @@ def main():
                     call, lim, what = cpu_arm(kind)
                     if call is None:
                         continue
-                    cores = pick_threads(call, sample_q(lim, 512, 3))
+                    cores = pick_threads(call, sample_q(lim, 512 if kind == "reference" else 8192, 3))
                     n_calls = 5
                     b = bounded_sample(call, lim, budget, n_calls)
                     times = time_cpu(call, sample_q(lim, b, 0), n_calls)

@@ -147,6 +147,11 @@ static int fk_jacobian_host_impl(const drmb200_topology_t* topo, int32_t ee_link
     if (batch == 0) return DRMB200_OK;
     const int n = topo->n_dofs;
     std::lock_guard<std::mutex> lock(g_pipe_mu);
+    struct DeviceGuard {                  // the caller's current device is restored on every return path
+        int prev = -1;
+        DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } }
+        ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    } guard;
     CK(cudaSetDevice(device));
     // Fused path: when every host buffer is page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) it has a
     // device alias under unified addressing, and the kernel's own TMA bulk copies read the q tiles from and write the

@@ -26,6 +26,7 @@
 //
 // Algorithmic HBM bytes per configuration: 4n (q) + 12 (pos) + 16 (quat) + 24n (J) = 28n + 28
 // (224 B for the 7-DoF Kuka iiwa) -- SURVEY.md section 8(d).
+#include <cstring>
 #include <mutex>
 #include "drm_common.cuh"
 
@@ -564,9 +565,25 @@ static int pdl_mode_for_launch(const PathProgram& prog, const FkArgs& args, int 
 
 int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const float* table, const float* q,
                        int64_t batch, float* pos, float* quat, float* jlin, float* jang, cudaStream_t stream) {
-    PathProgram prog;
-    int rc = build_path_program(topo, ee_link, &prog);
-    if (rc != DRMB200_OK) return rc;
+    // the path program depends only on (topology, ee_link): keep the last few per thread instead of rebuilding the
+    // 1.8 KB structure (and its signed gather map) on every call -- first-order for batch-1 calls
+    struct CachedProgram { bool valid; int32_t ee; drmb200_topology_t topo; PathProgram prog; };
+    static thread_local CachedProgram cache[4] = {};
+    static thread_local int cache_next = 0;
+    if (topo == nullptr) { set_error("topology is null"); return DRMB200_EINVAL; }
+    const PathProgram* cached = nullptr;
+    for (auto& c : cache)
+        if (c.valid && c.ee == ee_link && memcmp(&c.topo, topo, sizeof(*topo)) == 0) { cached = &c.prog; break; }
+    if (cached == nullptr) {
+        CachedProgram& c = cache[cache_next];
+        c.valid = false;
+        int rc = build_path_program(topo, ee_link, &c.prog);
+        if (rc != DRMB200_OK) return rc;
+        c.topo = *topo; c.ee = ee_link; c.valid = true;
+        cache_next = (cache_next + 1) & 3;
+        cached = &c.prog;
+    }
+    const PathProgram& prog = *cached;
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
     if ((jlin == nullptr) != (jang == nullptr)) { set_error("jac_lin and jac_ang must both be given or both be null"); return DRMB200_EINVAL; }
     if (batch == 0) return DRMB200_OK;

@@ -107,6 +107,7 @@ def _stream():
 
 
 def _require_cuda(*tensors):
+    first = None
     for t in tensors:
         if t is None:
             continue
@@ -117,6 +118,10 @@ def _require_cuda(*tensors):
             )
         if t.dtype != torch.float32:
             raise RuntimeError(f"the engine is fp32-only like the reference (got {t.dtype})")
+        if first is None:
+            first = t.device
+        elif t.device != first:
+            raise RuntimeError(f"all tensors of one call must live on the same GPU (got {first} and {t.device})")
 
 
 def launch_count():
@@ -194,6 +199,21 @@ def fk_jacobian_host(topo, ee_link, device_index, table, q_host, pos, quat, jlin
     """Host-buffer FK+Jacobian (H2D / kernel / D2H pipelined inside the library)."""
     _require_cuda(table)
     B = q_host.shape[0]
+    n = topo.n_dofs
+    for name, t, shape in (("q", q_host, (B, n)), ("pos", pos, (B, 3)), ("quat", quat, (B, 4)),
+                           ("jac_lin", jlin, (B, 3, n)), ("jac_ang", jang, (B, 3, n))):
+        if t is None:
+            if name == "q":
+                raise RuntimeError("q_host is required")
+            continue
+        if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != shape:
+            raise RuntimeError(f"{name}: expected a contiguous fp32 CPU tensor of shape {shape}, got "
+                               f"{t.dtype} {tuple(t.shape)} on {t.device} (contiguous={t.is_contiguous()})")
+    if table.device.index != device_index:
+        raise RuntimeError(f"table lives on {table.device}, the call targets cuda:{device_index}")
+    # the library launches on its own non-blocking stream: everything queued on torch's current stream of that device
+    # (e.g. the kernel that built `table`) must have completed first
+    torch.cuda.current_stream(table.device).synchronize()
     rc = lib().drmb200_fk_jacobian_host(ctypes.byref(topo), ee_link, device_index, _ptr(table), _ptr(q_host), B,
                                         _ptr(pos), _ptr(quat), _ptr(jlin), _ptr(jang))
     _check(rc, "drmb200_fk_jacobian_host")

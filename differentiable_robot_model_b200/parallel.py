@@ -39,12 +39,28 @@ def shard_rows(t: torch.Tensor, rank: int = None, world: int = None) -> torch.Te
 
 
 def broadcast_link_table(model, src: int = 0) -> torch.Tensor:
-    """Broadcast rank ``src``'s link table and pin it as every rank's cached table."""
+    """Make every rank compute with rank ``src``'s link parameters and return the (now identical) link table.
+
+    Constant models: ONE broadcast of the < 8 KB table, pinned as every rank's cached table.  Models with learnable
+    link parameters rebuild their table from the parameters on every call, so there the PARAMETERS (and buffers) of the
+    parametrisation modules are broadcast instead -- one flat buffer -- and the table follows from them."""
+    active = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    state = [t for t in list(model.parameters()) + list(model.buffers())]
+    if state and model._any_learnable_module():
+        flat = torch.cat([t.detach().reshape(-1).to(torch.float32) for t in state])
+        if active:
+            dist.broadcast(flat, src=src)
+        off = 0
+        with torch.no_grad():
+            for t in state:
+                n = t.numel()
+                t.copy_(flat[off:off + n].view_as(t).to(t.dtype))
+                off += n
+        return model._link_table().detach()
     table = model._link_table().detach().clone()
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if active:
         dist.broadcast(table, src=src)
     model._table_cache = table
-    model._table_cache_key = tuple((p.data_ptr(), p._version) for p in model.parameters())
     return table
 
 

@@ -86,7 +86,13 @@ class DifferentiableRobotModel(torch.nn.Module):
     def __init__(self, urdf_path: str, name="", device=None):
         super().__init__()
         self.name = name
-        self._device = torch.device(device) if device is not None else torch.device("cpu")
+        # device=None: the reference defaults to the CPU and computes there (robot_model.py:100-104).  This engine has
+        # no CPU path, so a default-constructed model lives on the current CUDA device whenever one is present (and
+        # computes, like the reference's default-constructed model does); without a GPU it is a host-side model
+        # (URDF, topology, parameters, joint limits) whose compute entry points raise.  An explicit device is honoured.
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self._device = torch.device(device)
         if self._device.type == "cuda" and self._device.index is None:
             self._device = torch.device("cuda", torch.cuda.current_device())
 
@@ -122,7 +128,7 @@ class DifferentiableRobotModel(torch.nn.Module):
         self._topology = compile_topology(self._bodies, self._parent_idx)
         self._kin_state = None
         self._table_cache = None
-        self._table_cache_key = None
+        self._has_learnable = None          # any of the six per-link attributes replaced by a torch.nn.Module
 
     # ------------------------------------------------------------------------------------------
     # link table
@@ -141,20 +147,33 @@ class DifferentiableRobotModel(torch.nn.Module):
         finally:
             self._shared_table = None
 
+    def invalidate_link_table(self) -> None:
+        """Drop the cached link table (call after editing a constant link parameter tensor in place)."""
+        self._table_cache = None
+        self._has_learnable = None
+
+    def _any_learnable_module(self) -> bool:
+        if self._has_learnable is None:
+            self._has_learnable = any(
+                isinstance(getattr(owner, name), torch.nn.Module)
+                for body in self._bodies
+                for owner, names in ((body, ("trans", "rot_angles", "joint_damping")), (body.inertia, ("mass", "com", "inertia_mat")))
+                for name in names)
+        return self._has_learnable
+
     def _link_table(self) -> torch.Tensor:
-        """The ``[n_links, 28]`` device table.  Constant models build it once; with learnable link
-        parameters it is rebuilt (differentiably) whenever a parameter changed or a graph is needed."""
+        """The ``[n_links, 28]`` device table.  A model whose link parameters are all URDF constants builds it once.
+        As soon as any link parameter is a parametrisation module the table is re-evaluated on EVERY call (one
+        ``torch.cat`` + one kernel), exactly like the reference re-evaluates its per-link callables on every call --
+        in-place edits of parameters (``p.data.copy_``), buffers or frozen modules can never leave a stale table behind;
+        the result carries an autograd graph when grad mode is on and a parameter requires grad."""
         if getattr(self, "_shared_table", None) is not None:
             return self._shared_table
-        params = list(self.parameters())
-        needs_graph = torch.is_grad_enabled() and any(p.requires_grad for p in params)
-        if needs_graph:
+        if self._any_learnable_module():
             return build_link_table(self._bodies, self._device)
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        if self._table_cache is None or self._table_cache_key != key:
+        if self._table_cache is None:
             with torch.no_grad():
                 self._table_cache = build_link_table(self._bodies, self._device)
-            self._table_cache_key = key
         return self._table_cache
 
     def _kinematic_params_learnable(self) -> bool:
@@ -399,7 +418,7 @@ class DifferentiableRobotModel(torch.nn.Module):
         owner = self._get_parent_object_of_param(link_name, parameter_name)
         owner.__delattr__(parameter_name)
         owner.add_module(parameter_name, parametrization.to(self._device))
-        self._table_cache = None
+        self.invalidate_link_table()
 
     def _learnable_module(self, link_name: str, parameter_name: str):
         owner = self._get_parent_object_of_param(link_name, parameter_name)

@@ -307,3 +307,93 @@ def test_host_buffer_entry_point_matches_device_path(mode):
     want = m.compute_fk_and_jacobian(q_host.to(DEV), "iiwa_link_ee")
     for got, w in zip(outs, want):
         assert torch.equal(got, w.cpu())
+
+
+# ------------------------------------------------------------------------------------------------
+# programmatic dependent launch (fk_pdl = 2): launches overlap their predecessors; results must not change
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture
+def pdl_mode():
+    engine.set_option("fk_pdl", 2)
+    yield
+    engine.set_option("fk_pdl", 0)
+
+
+def _fk_reference_runs(m, ee, qs):
+    engine.set_option("fk_pdl", 0)
+    want = [[t.clone() for t in engine.fk_jacobian_raw(m._topology, ee, m._link_table(), q)] for q in qs]
+    torch.cuda.synchronize()
+    return want
+
+
+@pytest.mark.parametrize("batch", [65536, 40000, 4099])
+def test_pdl_chain_of_independent_batches_is_bit_identical(batch, pdl_mode):
+    """A stream of back-to-back FK launches over rotating buffers, eagerly and replayed from a CUDA graph, with the
+    launches overlapping (batch >= ~30 k takes the PDL path, smaller ones fall back): outputs == ordinary launches."""
+    m = gpu_model("iiwa7")
+    ee = m._name_to_idx_map["iiwa_link_ee"]
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float32)
+    qs = [O.sample_inputs(robot, batch, seed=40 + i)[0].to(DEV) for i in range(6)]
+    want = _fk_reference_runs(m, ee, qs)
+    engine.set_option("fk_pdl", 2)
+    table = m._link_table()
+    outs = [tuple(torch.zeros_like(t) for t in w) for w in want]
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        for rep in range(3):
+            for i, q in enumerate(qs):
+                engine.fk_jacobian_raw(m._topology, ee, table, q, out=outs[i])
+        stream.synchronize()
+        for w, o in zip(want, outs):
+            for a, b in zip(w, o):
+                assert torch.equal(a, b)
+                b.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for rep in range(4):
+                for i, q in enumerate(qs):
+                    engine.fk_jacobian_raw(m._topology, ee, table, q, out=outs[i])
+        for _ in range(3):
+            g.replay()
+        stream.synchronize()
+    for w, o in zip(want, outs):
+        for a, b in zip(w, o):
+            assert torch.equal(a, b)
+
+
+def test_pdl_falls_back_when_a_launch_reads_its_predecessors_output(pdl_mode):
+    """Launch k+1 takes the J_lin block that launch k is still writing as its q: stream order must hold."""
+    m = gpu_model("iiwa7")
+    ee = m._name_to_idx_map["iiwa_link_ee"]
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float32)
+    B = 65536
+    q0 = O.sample_inputs(robot, B, seed=77)[0].to(DEV)
+    table = m._link_table()
+
+    def chain():
+        cur, res = q0, []
+        for _ in range(4):
+            pos, quat, jl, ja = engine.fk_jacobian_raw(m._topology, ee, table, cur)
+            res.append((pos, quat, jl, ja))
+            cur = jl.view(3 * B, 7)[:B]                 # the first B rows of the block just written, as joint angles
+        torch.cuda.synchronize()
+        return res
+
+    engine.set_option("fk_pdl", 0)
+    want = chain()
+    engine.set_option("fk_pdl", 2)
+    for _ in range(3):
+        got = chain()
+        for w, g_ in zip(want, got):
+            for a, b in zip(w, g_):
+                assert torch.equal(a, b)
+
+
+def test_default_constructed_model_computes():
+    """The reference's default-constructed model computes (on its default device, robot_model.py:100-104); here the
+    default device is the current CUDA device."""
+    m = drm.DifferentiableKUKAiiwa()
+    assert m._device.type == "cuda"
+    g = load_golden("iiwa7")
+    pos, quat = m.compute_forward_kinematics(cuda(g["q"]), "iiwa_link_ee")
+    assert_close(pos.cpu().numpy(), g["pos.iiwa_link_ee"], what="pos")

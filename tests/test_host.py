@@ -137,13 +137,20 @@ def test_learnable_parameter_plumbing():
     assert not m._bodies[1].inertia.mass.l.requires_grad
     m.unfreeze_learnable_link_param("iiwa_link_1", "mass")
     assert m._bodies[1].inertia.mass.l.requires_grad
-    # cache follows parameter updates when no graph is needed
+    # a model with parametrisation modules re-evaluates them on every call (like the reference), so edits that do
+    # not bump a Parameter's version counter (p.data.copy_) can never leave a stale table behind
     with torch.no_grad():
         t1 = m._link_table()
-        assert m._link_table() is t1
-        m._bodies[2].trans.param.add_(1.0)
+        assert torch.equal(m._link_table(), t1)
+        m._bodies[2].trans.param.data.add_(1.0)
         t2 = m._link_table()
         assert not torch.equal(t1, t2)
+    # a constant model builds its table once; in-place edits of the URDF constants need invalidate_link_table()
+    c = drm.DifferentiableKUKAiiwa()
+    t1 = c._link_table()
+    assert c._link_table() is t1
+    c.invalidate_link_table()
+    assert c._link_table() is not t1 and torch.equal(c._link_table(), t1)
 
 
 def test_fixed_joint_origin_is_frozen_like_the_reference():

@@ -45,15 +45,24 @@ def _worker(rank, world, port, out_dir):
     model.make_link_param_learnable("iiwa_link_1", "mass", UnconstrainedScalar())
     model.make_link_param_learnable("iiwa_link_2", "trans", UnconstrainedTensor(dim1=1, dim2=3))
 
-    # (1) the single broadcast: every rank ends up with rank 0's table, cached
+    # (1) the single broadcast.  Learnable model: the PARAMETERS are broadcast, so every later (differentiable) table
+    # build on every rank starts from rank 0's values
     mine = model._link_table().detach().clone()
     table = parallel.broadcast_link_table(model, src=0)
     gathered = [torch.empty_like(table) for _ in range(world)]
     dist.all_gather(gathered, table)
     assert all(torch.equal(g, gathered[0]) for g in gathered)
     assert (rank == 0) == torch.equal(mine, table)
-    with torch.no_grad():
-        assert model._link_table() is table
+    rebuilt = model._link_table()                       # grad mode on: rebuilt from the (now identical) parameters
+    assert rebuilt.requires_grad and torch.equal(rebuilt.detach(), table)
+    params = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    all_params = [torch.empty_like(params) for _ in range(world)]
+    dist.all_gather(all_params, params)
+    assert all(torch.equal(a, all_params[0]) for a in all_params)
+    # constant model: the table itself is broadcast and pinned
+    const = drm.DifferentiableRobotModel(urdf_path("iiwa7"), "c")
+    t = parallel.broadcast_link_table(const, src=0)
+    assert const._link_table() is t
 
     # (2) sharding: shards of a replicated tensor reassemble to the original
     full = torch.arange(11 * 7, dtype=torch.float32).reshape(11, 7)

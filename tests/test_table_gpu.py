@@ -13,7 +13,7 @@ DEV = "cuda:0"
 
 def test_fused_table_matches_torch_assembly(robot_stem):
     gpu = drm.DifferentiableRobotModel(urdf_path(robot_stem), robot_stem, device=DEV)
-    cpu = drm.DifferentiableRobotModel(urdf_path(robot_stem), robot_stem)
+    cpu = drm.DifferentiableRobotModel(urdf_path(robot_stem), robot_stem, device="cpu")
     launches = engine.launch_count()
     t_gpu = gpu._link_table()
     assert engine.launch_count() - launches == 1                 # one kernel, not ~60 torch launches
