@@ -87,3 +87,17 @@ def canon_quat(q):
     idx = np.argmax(np.abs(q), axis=-1)
     sign = np.sign(np.take_along_axis(q, idx[..., None], axis=-1))
     return q * sign
+
+
+LARGE_GOLDEN = {"large_iiwa7": "iiwa7", "large_panda_no_gripper": "panda_no_gripper", "large_allegro_left": "allegro_hand_description_left"}
+
+
+def quat_branch_margin(R):
+    """How far each rotation matrix is from a decision boundary of the reference's get_quaternion branch structure
+    (spatial_vector_algebra.py:118-128): min(|trace|, gaps between the diagonal elements the else-branch compares).
+    Rows with a clear margin must reproduce the reference's RAW quaternion, sign included."""
+    R = np.asarray(R, dtype=np.float64)
+    tr = R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    d = np.stack([R[:, 0, 0], R[:, 1, 1], R[:, 2, 2]], axis=1)
+    gaps = np.minimum(np.abs(d[:, 0] - d[:, 1]), np.minimum(np.abs(d[:, 1] - d[:, 2]), np.abs(d[:, 0] - d[:, 2])))
+    return np.where(tr > 0, np.abs(tr), np.minimum(np.abs(tr), gaps))

@@ -397,3 +397,30 @@ def test_default_constructed_model_computes():
     g = load_golden("iiwa7")
     pos, quat = m.compute_forward_kinematics(cuda(g["q"]), "iiwa_link_ee")
     assert_close(pos.cpu().numpy(), g["pos.iiwa_link_ee"], what="pos")
+
+
+# ------------------------------------------------------------------------------------------------
+# 1024-row reference batches, raw quaternion sign on all four branches of get_quaternion
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stem", ["large_iiwa7", "large_panda_no_gripper", "large_allegro_left"])
+def test_large_reference_batches_with_raw_quaternion_sign(stem, fk_variant):
+    from conftest import LARGE_GOLDEN, quat_branch_margin
+    g = load_golden(stem)
+    m = gpu_model(LARGE_GOLDEN[stem])
+    q, qd, qdd = cuda(g["q"]), cuda(g["qd"]), cuda(g["qdd"])
+    for link in g["links"].tolist():
+        pos, quat, jl, ja = m.compute_fk_and_jacobian(q, link)
+        assert_close(pos.cpu().numpy(), g[f"pos.{link}"], what=f"{stem} pos {link}")
+        assert_close(jl.cpu().numpy(), g[f"jlin.{link}"], what=f"{stem} jlin {link}")
+        assert_close(ja.cpu().numpy(), g[f"jang.{link}"], what=f"{stem} jang {link}")
+        # the RAW quaternion (sign included) wherever the rotation is clear of a branch boundary of
+        # spatial_vector_algebra.py:118-128; the remaining rows up to sign
+        clear = quat_branch_margin(g[f"R.{link}"]) > 1e-3
+        assert_close(quat.cpu().numpy()[clear], g[f"quat.{link}"][clear], atol=2e-6, what=f"{stem} raw quat {link}")
+        assert_close(canon_quat(quat.cpu().numpy()), canon_quat(g[f"quat.{link}"]), atol=2e-6, what=f"{stem} quat {link}")
+    if stem != "large_allegro_left":
+        branch = g["branch"]
+        clear = quat_branch_margin(g[f"R.{g['links'][0]}"]) > 1e-3
+        assert min(int((clear & (branch == b)).sum()) for b in range(4)) >= 40      # each branch asserted with raw sign
+    tau = m.compute_inverse_dynamics(q, qd, qdd)
+    assert_close(tau.cpu().numpy(), g["tau"], atol=1e-5, what=f"{stem} tau")
