@@ -32,6 +32,9 @@ static const Option g_option_table[] = {
                                                  //    an input overlaps an output of the launches still in flight, see
                                                  //    pdl_mode_for_launch in fk_jacobian.cu); 1 = wait before the first global
                                                  //    read (A/B only: measured slower than 0)
+    {"tree_warps", "DRMB200_TREE_WARPS", 0},     // 8: multi-ee tree kernel: warps per CTA (1..4), 0 = auto
+    {"tree_grid_cap", "DRMB200_TREE_GRID_CAP", 0},   // 9: multi-ee tree kernel: resident CTAs per SM, 0 = as many as fit
+    {"tree_bufs", "DRMB200_TREE_BUFS", 1},       // 10: multi-ee tree kernel: output tiles per warp (1 or 2)
 };
 constexpr int N_OPTIONS = sizeof(g_option_table) / sizeof(g_option_table[0]);
 static std::atomic<int> g_options[N_OPTIONS];
@@ -67,6 +70,8 @@ static int set_option_by_name(const char* name, int value) {
 // implemented in the kernel translation units
 int fk_jacobian_device(const drmb200_topology_t*, int32_t, const float*, const float*, int64_t, float*, float*,
                        float*, float*, cudaStream_t);
+int fk_jacobian_multi_device(const drmb200_topology_t*, int32_t, const int32_t*, const float*, const float*, int64_t, float*,
+                             float*, float*, float*, cudaStream_t);
 int fk_jacobian_backward_device(const drmb200_topology_t*, int32_t, const float*, const float*, int64_t,
                                 const float*, const float*, const float*, const float*, float*, float*, void*,
                                 cudaStream_t);
@@ -234,6 +239,13 @@ int drmb200_fk_jacobian(const drmb200_topology_t* topo, int32_t ee_link, const f
                         int64_t batch, float* pos, float* quat, float* jac_lin, float* jac_ang, void* cuda_stream) {
     return drm::fk_jacobian_device(topo, ee_link, table, q, batch, pos, quat, jac_lin, jac_ang,
                                    static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_fk_jacobian_multi(const drmb200_topology_t* topo, int32_t n_ee, const int32_t* ee_links, const float* table,
+                              const float* q, int64_t batch, float* pos, float* quat, float* jac_lin, float* jac_ang,
+                              void* cuda_stream) {
+    return drm::fk_jacobian_multi_device(topo, n_ee, ee_links, table, q, batch, pos, quat, jac_lin, jac_ang,
+                                         static_cast<cudaStream_t>(cuda_stream));
 }
 
 int64_t drmb200_table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch) {

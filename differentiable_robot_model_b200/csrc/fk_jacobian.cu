@@ -406,6 +406,9 @@ fk_jacobian_kernel(const __grid_constant__ PathProgram prog, const FkArgs args) 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+int fk_jacobian_multi_device(const drmb200_topology_t*, int32_t, const int32_t*, const float*, const float*, int64_t, float*,
+                             float*, float*, float*, cudaStream_t);      // fk_tree.cu
+
 int build_path_program(const drmb200_topology_t* topo, int32_t ee_link, PathProgram* prog) {
     if (topo == nullptr) { set_error("topology is null"); return DRMB200_EINVAL; }
     if (topo->n_links < 1 || topo->n_links > DRMB200_MAX_LINKS) {
@@ -597,6 +600,12 @@ int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const fl
     args.aligned = (al16(q) && al16(pos) && al16(quat) && al16(jlin) && al16(jang)) ? 1 : 0;
     args.use_bulk = get_option(0) != 0;
     const bool with_jac = jlin != nullptr;
+    // n_dofs % 4 == 0 (Allegro, n = 16): the per-lane rows of this kernel's natural-layout tiles are 16-way bank
+    // conflicts; the tree-walk kernel (fk_tree.cu) assembles 16-byte column chunks instead.  Measured, one Allegro
+    // fingertip (profiles/r02): 2^21 per launch 0.78 of the HBM roofline there vs 0.71 here (unrolled variant); 32 768 per
+    // launch 0.57 there vs 0.63 here -- so large batches are routed to the tree kernel, small ones stay.
+    if ((prog.n_dofs & 3) == 0 && prog.n_dofs > 0 && batch >= 262144 && get_option(2) == 2)
+        return fk_jacobian_multi_device(topo, 1, &ee_link, table, q, batch, pos, quat, jlin, jang, stream);
     args.pdl = pdl_mode_for_launch(prog, args, topo->n_links, stream);
 
 

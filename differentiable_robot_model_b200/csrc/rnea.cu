@@ -228,10 +228,15 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
         }
 
         // ---- pass 2: leaves -> root, wrench propagation + joint torques (robot_model.py:284-301, 353-373)
+        // The wrench a link hands to its parent travels in REGISTERS when the parent is the link processed next
+        // (parent == i - 1: always, on a chain); only children of far branch points accumulate into their parent's
+        // shared-memory slot.  prog.tip[i] < 0 says that link i + 1 is a child of i, i.e. `carry` is meant for link i.
+        V3 carry_f = zero, carry_n = zero;
         for (int i = N - 1; i >= 1; --i) {
             const uint32_t lk = a_link + i * 8 * E;
-            const V3 f = ldv_s(lk);
-            const V3 nn = ldv_s(lk + 3 * E);
+            V3 f = ldv_s(lk);
+            V3 nn = ldv_s(lk + 3 * E);
+            if (i + 1 < N && prog.tip[i] < 0) { f = f + carry_f; nn = nn + carry_n; }
             const int c = prog.dof[i];
             const uint32_t row = a_tab + i * (DRMB200_TABLE_STRIDE * 4);
             if (c >= 0) {
@@ -252,9 +257,13 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
                     fp = mul(F, rotz(f, cs, sn));
                     np = cross_add(r, fp, mul(F, rotz(nn, cs, sn)));
                 }
-                const uint32_t pk = a_link + p * 8 * E;
-                stv_s(pk, ldv_s(pk) + fp);
-                stv_s(pk + 3 * E, ldv_s(pk + 3 * E) + np);
+                if (p == i - 1) {
+                    carry_f = fp; carry_n = np;
+                } else {
+                    const uint32_t pk = a_link + p * 8 * E;
+                    stv_s(pk, ldv_s(pk) + fp);
+                    stv_s(pk + 3 * E, ldv_s(pk + 3 * E) + np);
+                }
             }
         }
     }

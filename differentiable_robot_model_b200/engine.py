@@ -33,6 +33,9 @@ _SIGNATURES = {
     "drmb200_fk_jacobian": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, _c_float_p, _c_float_p,
                                            ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                            ctypes.c_void_p]),
+    "drmb200_fk_jacobian_multi": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, ctypes.POINTER(ctypes.c_int32),
+                                                 _c_float_p, _c_float_p, ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p,
+                                                 _c_float_p, ctypes.c_void_p]),
     "drmb200_table_grad_workspace_bytes": (ctypes.c_int64, [ctypes.POINTER(Topology), ctypes.c_int64]),
     "drmb200_fk_jacobian_backward": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, _c_float_p, _c_float_p,
                                                     ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
@@ -151,6 +154,27 @@ def fk_jacobian_raw(topo, ee_link, table, q, want_pos=True, want_quat=True, want
         rc = lib().drmb200_fk_jacobian(ctypes.byref(topo), ee_link, _ptr(table), _ptr(q), B, _ptr(pos), _ptr(quat),
                                        _ptr(jlin), _ptr(jang), _stream())
     _check(rc, "drmb200_fk_jacobian")
+    return pos, quat, jlin, jang
+
+
+def fk_jacobian_multi_raw(topo, ee_links, table, q, want_pos=True, want_quat=True, want_jac=True, out=None):
+    """FK (+ Jacobians) of several links in ONE tree walk (drmb200_fk_jacobian_multi): stacked [n_ee, B, ...] outputs."""
+    _require_cuda(table, q)
+    q = q.contiguous()
+    B, n = q.shape
+    dev, E = q.device, len(ee_links)
+    if out is not None:
+        pos, quat, jlin, jang = out
+    else:
+        pos = torch.empty((E, B, 3), device=dev, dtype=torch.float32) if want_pos else None
+        quat = torch.empty((E, B, 4), device=dev, dtype=torch.float32) if want_quat else None
+        jlin = torch.empty((E, B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
+        jang = torch.empty((E, B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
+    links = (ctypes.c_int32 * E)(*[int(l) for l in ee_links])
+    with torch.cuda.device(dev):
+        rc = lib().drmb200_fk_jacobian_multi(ctypes.byref(topo), E, links, _ptr(table), _ptr(q), B, _ptr(pos), _ptr(quat),
+                                             _ptr(jlin), _ptr(jang), _stream())
+    _check(rc, "drmb200_fk_jacobian_multi")
     return pos, quat, jlin, jang
 
 
@@ -281,6 +305,43 @@ class FkJacobianFunction(torch.autograd.Function):
                                                     _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _ptr(q_grad),
                                                     _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_fk_jacobian_backward")
+        return table_grad, q_grad, None, None, None, None, None
+
+
+class FkJacobianMultiFunction(torch.autograd.Function):
+    """(table, q) -> stacked (pos, quat, jac_lin, jac_ang) of several links: one tree-walk launch forward; the adjoint is
+    the sum of the single-link adjoints, one launch of the FK backward kernel per link with a non-zero upstream gradient
+    (q_grad summed, table_grad accumulated in place by the kernel)."""
+
+    @staticmethod
+    def forward(ctx, table, q, topo, ee_links, want_pos, want_quat, want_jac):
+        table, q = table.contiguous(), q.contiguous()
+        outs = fk_jacobian_multi_raw(topo, ee_links, table, q, want_pos, want_quat, want_jac)
+        ctx.save_for_backward(table, q)
+        ctx.topo, ctx.ee_links = topo, tuple(ee_links)
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_pos, g_quat, g_jlin, g_jang):
+        table, q = ctx.saved_tensors
+        need_table, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        B, n = q.shape
+        table_grad = torch.zeros_like(table) if need_table else None
+        q_grad = torch.zeros_like(q) if need_q else None
+        ws = _workspace(ctx.topo, B, q.device)
+        for e, link in enumerate(ctx.ee_links):
+            g = [None if t is None else t[e].contiguous() for t in (g_pos, g_quat, g_jlin, g_jang)]
+            if all(t is None for t in g):
+                continue
+            _require_cuda(*g)
+            q_grad_e = torch.empty_like(q) if need_q else None
+            with torch.cuda.device(q.device):
+                rc = lib().drmb200_fk_jacobian_backward(ctypes.byref(ctx.topo), int(link), _ptr(table), _ptr(q), B,
+                                                        _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _ptr(q_grad_e),
+                                                        _ptr(table_grad), _ptr(ws), _stream())
+            _check(rc, "drmb200_fk_jacobian_backward")
+            if need_q:
+                q_grad += q_grad_e
         return table_grad, q_grad, None, None, None, None, None
 
 

@@ -241,6 +241,36 @@ class DifferentiableRobotModel(torch.nn.Module):
         self._check_q(q)
         return self._fk_jacobian(q, link_name, True, True, True)
 
+    def _fk_jacobian_multi(self, q, link_names, want_pos, want_quat, want_jac):
+        links = [self._name_to_idx_map[name] for name in link_names]      # KeyError for unknown links
+        assert len(set(links)) == len(links), "link names must be distinct"
+        table = self._link_table()
+        if torch.is_grad_enabled() and (q.requires_grad or table.requires_grad):
+            return engine.FkJacobianMultiFunction.apply(table, q, self._topology, links, want_pos, want_quat, want_jac)
+        return engine.fk_jacobian_multi_raw(self._topology, links, table, q, want_pos, want_quat, want_jac)
+
+    @tensor_check
+    def compute_fk_and_jacobian_multi(
+        self, q: torch.Tensor, link_names: List[str]
+    ) -> Dict[str, Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]]:
+        r"""``{link_name: (pos, quat, lin_jac, ang_jac)}`` of several links (at most 8, distinct) from ONE launch that walks
+        the union of their root paths once per configuration (``csrc/fk_tree.cu``) -- e.g. the four fingertips of a hand.
+        Every entry equals what ``compute_forward_kinematics`` / ``compute_endeffector_jacobian`` return for that link
+        (the reference runs its whole per-link pass once per end effector, ``robot_model.py:641``).  Differentiable.
+        Like ``compute_forward_kinematics_all_links``, 1-D inputs give un-squeezed ``[1, .]`` values."""
+        self._check_q(q)
+        pos, quat, jlin, jang = self._fk_jacobian_multi(q, link_names, True, True, True)
+        return {name: (pos[e], quat[e], jlin[e], jang[e]) for e, name in enumerate(link_names)}
+
+    @tensor_check
+    def compute_endeffector_jacobians(
+        self, q: torch.Tensor, link_names: List[str]
+    ) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
+        r"""``{link_name: (lin_jac, ang_jac)}`` of several links from one launch (see ``compute_fk_and_jacobian_multi``)."""
+        self._check_q(q)
+        _, _, jlin, jang = self._fk_jacobian_multi(q, link_names, False, False, True)
+        return {name: (jlin[e], jang[e]) for e, name in enumerate(link_names)}
+
     # ------------------------------------------------------------------------------------------
     # dynamics
     # ------------------------------------------------------------------------------------------

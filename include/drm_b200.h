@@ -117,6 +117,19 @@ int drmb200_fk_jacobian(const drmb200_topology_t* topo, int32_t ee_link,
                         void* cuda_stream);
 
 /*
+ * FK (+ geometric Jacobians) of SEVERAL links in one walk of the kinematic tree: the union of the root -> link paths is
+ * walked once per configuration and every requested link emits its outputs as the walk passes it (hands and multi-limb
+ * robots: BASELINE config 4 evaluates the four Allegro fingertips; the reference needs one compute_endeffector_jacobian
+ * call -- and one full update_kinematic_state pass, robot_model.py:140-195 -- per fingertip).
+ *   ee_links [n_ee]  host array of distinct link indices, 1 <= n_ee <= 8 (the root is allowed);
+ *   outputs          pos [n_ee, B, 3], quat [n_ee, B, 4], jac_lin / jac_ang [n_ee, B, 3, n_dofs]; block e equals what
+ *                    drmb200_fk_jacobian returns for ee_links[e] (bit for bit); NULL skips an output as above.
+ */
+int drmb200_fk_jacobian_multi(const drmb200_topology_t* topo, int32_t n_ee, const int32_t* ee_links,
+                              const float* table, const float* q, int64_t batch,
+                              float* pos, float* quat, float* jac_lin, float* jac_ang, void* cuda_stream);
+
+/*
  * Adjoint of drmb200_fk_jacobian.  g_* are the upstream gradients of the corresponding outputs
  * (NULL = zero).  Writes q_grad [B, n_dofs] (may be NULL) and accumulates the batch-summed
  * gradient of the table into table_grad [n_links, 28] (may be NULL; must be zero-initialised or

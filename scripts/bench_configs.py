@@ -227,6 +227,24 @@ def bench_fk(model, link, batch):
             "hbm_frac": batch * by / ms / 1e6 / PEAK}
 
 
+def bench_fk_multi(model, links, batch):
+    """config 4 fused: (pos, quat, J_lin, J_ang) of several links from ONE tree-walk launch (csrc/fk_tree.cu)."""
+    robot = O.load_robot(model.urdf_path if hasattr(model, "urdf_path") else model._urdf_path, torch.float32)
+    n, E = robot.n_dofs, len(links)
+    by = 4 * n + E * (28 + 24 * n)
+    R = min(rotate_count(batch * by), 8)
+    qs = [O.sample_inputs(robot, batch, seed=r)[0].to(DEV) for r in range(R)]
+    outs = [(torch.empty(E, batch, 3, device=DEV), torch.empty(E, batch, 4, device=DEV), torch.empty(E, batch, 3, n, device=DEV),
+             torch.empty(E, batch, 3, n, device=DEV)) for _ in range(R)]
+    table, topo = model._link_table(), model._topology
+    ees = [model._name_to_idx_map[l] for l in links]
+    ms = timed(lambda i: engine.fk_jacobian_multi_raw(topo, ees, table, qs[i % R], out=outs[i % R]),
+               200 if batch <= (1 << 17) else 20)
+    return {"batch": batch, "links": links, "ms": ms, "configs_per_s": batch / ms * 1e3,
+            "algorithmic_bytes_per_config": by, "achieved_GBps": batch * by / ms / 1e6,
+            "hbm_frac": batch * by / ms / 1e6 / PEAK}
+
+
 def bench_backward_kernels(batch):
     """Raw launches of the analytic adjoint kernels (Kuka): FK/Jacobian backward, full RNEA backward, inertial-only."""
     import ctypes
@@ -334,6 +352,16 @@ def bench_train_step(batch):
 
 def main():
     out = {"peak_GBps": PEAK, "gpu": torch.cuda.get_device_name(0)}
+    if os.environ.get("BENCH_ONLY") == "config4":
+        allegro = drm.DifferentiableRobotModel(os.path.join(drm.robot_model.robot_description_folder,
+                                                            "allegro/urdf/allegro_hand_description_left.urdf"), device=DEV)
+        allegro.urdf_path = os.path.join(drm.robot_model.robot_description_folder, "allegro/urdf/allegro_hand_description_left.urdf")
+        tips = ["link_3.0_tip", "link_7.0_tip", "link_11.0_tip", "link_15.0_tip"]
+        out["config4_allegro_fk_jac"] = [bench_fk(allegro, "link_15.0_tip", b) for b in (32768, 1 << 21)]
+        out["config4_allegro_fk_jac_tree_kernel_one_tip"] = [bench_fk_multi(allegro, tips[3:], b) for b in (32768, 1 << 21)]
+        out["config4_allegro_fk_jac_fused_4_tips"] = [bench_fk_multi(allegro, tips, b) for b in (32768, 1 << 20)]
+        print(json.dumps(out))
+        return
     out["config3_panda_rnea"] = [bench_rnea(drm.DifferentiableFrankaPanda, b) for b in (65536, 1 << 21)]
     out["kuka_rnea"] = [bench_rnea(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 21)]
     engine.set_option("rnea_packed", 0)
@@ -344,6 +372,9 @@ def main():
     allegro.urdf_path = allegro._urdf_model and os.path.join(drm.robot_model.robot_description_folder,
                                                              "allegro/urdf/allegro_hand_description_left.urdf")
     out["config4_allegro_fk_jac"] = [bench_fk(allegro, "link_15.0_tip", b) for b in (32768, 1 << 21)]
+    tips = ["link_3.0_tip", "link_7.0_tip", "link_11.0_tip", "link_15.0_tip"]
+    out["config4_allegro_fk_jac_tree_kernel_one_tip"] = [bench_fk_multi(allegro, tips[3:], b) for b in (32768, 1 << 21)]
+    out["config4_allegro_fk_jac_fused_4_tips"] = [bench_fk_multi(allegro, tips, b) for b in (32768, 1 << 20)]
     out["config5_kuka_train_step"] = [bench_train_step(b) for b in (131072,)]
     out["kuka_backward_kernels"] = [bench_backward_kernels(131072)]
     out["kuka_mass_matrix"] = [bench_mass_matrix(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 20)]
