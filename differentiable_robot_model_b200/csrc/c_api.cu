@@ -77,6 +77,8 @@ int fk_jacobian_backward_device(const drmb200_topology_t*, int32_t, const float*
                                 cudaStream_t);
 int inverse_dynamics_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*,
                             int64_t, uint32_t, float*, cudaStream_t);
+int dynamic_state_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*, int64_t, uint32_t,
+                         float*, float*, float*, float*, cudaStream_t);
 int inverse_dynamics_backward_device(const drmb200_topology_t*, const float*, const float*, const float*,
                                      const float*, int64_t, uint32_t, const float*, float*, float*, float*,
                                      float*, void*, cudaStream_t);
@@ -91,6 +93,10 @@ int build_table_device(const float*, int32_t, float*, cudaStream_t);
 int kinematic_state_device(const drmb200_topology_t*, const float*, const float*, const float*, int64_t, float*, float*,
                            float*, cudaStream_t);
 int build_table_backward_device(const float*, const float*, int32_t, float*, cudaStream_t);
+int build_table_fused_device(const float*, const float*, const int32_t*, const int32_t*, const float*, int32_t, float*, float*,
+                             cudaStream_t);
+int build_table_fused_backward_device(const float*, const float*, const float*, const int32_t*, const int32_t*, int32_t, int32_t,
+                                      float*, float*, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // host-buffer pipeline for FK + Jacobian
@@ -266,6 +272,13 @@ int drmb200_inverse_dynamics(const drmb200_topology_t* topo, const float* table,
                                         static_cast<cudaStream_t>(cuda_stream));
 }
 
+int drmb200_dynamic_state(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                          const float* qdd, int64_t batch, uint32_t flags, float* tau, float* vels, float* accs,
+                          float* forces, void* cuda_stream) {
+    return drm::dynamic_state_device(topo, table, q, qd, qdd, batch, flags, tau, vels, accs, forces,
+                                     static_cast<cudaStream_t>(cuda_stream));
+}
+
 int drmb200_inverse_dynamics_backward(const drmb200_topology_t* topo, const float* table, const float* q,
                                       const float* qd, const float* qdd, int64_t batch, uint32_t flags,
                                       const float* g_tau, float* q_grad, float* qd_grad, float* qdd_grad,
@@ -310,6 +323,19 @@ int drmb200_build_link_table(const float* raw, int32_t n_links, float* table, vo
 int drmb200_build_link_table_backward(const float* raw, const float* table_grad, int32_t n_links, float* raw_grad,
                                       void* cuda_stream) {
     return drm::build_table_backward_device(raw, table_grad, n_links, raw_grad, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_build_link_table_fused(const float* const_raw, const float* flat, const int32_t* src, const int32_t* kind,
+                                   const float* off, int32_t n_links, float* raw_out, float* table, void* cuda_stream) {
+    return drm::build_table_fused_device(const_raw, flat, src, kind, off, n_links, raw_out, table,
+                                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_build_link_table_fused_backward(const float* raw, const float* table_grad, const float* flat, const int32_t* src,
+                                            const int32_t* kind, int32_t n_links, int32_t n_flat, float* raw_grad_scratch,
+                                            float* flat_grad, void* cuda_stream) {
+    return drm::build_table_fused_backward_device(raw, table_grad, flat, src, kind, n_links, n_flat, raw_grad_scratch, flat_grad,
+                                                  static_cast<cudaStream_t>(cuda_stream));
 }
 
 int drmb200_fk_jacobian_host(const drmb200_topology_t* topo, int32_t ee_link, int32_t device, const float* table,

@@ -27,6 +27,7 @@
 //
 // Algorithmic HBM bytes per configuration: 12n in + 4n out = 16n (112 B at n = 7).  At roughly
 // 2 kflop per 7-DoF configuration the kernel is FP32-issue-bound, not HBM-bound.
+#include <cstring>
 #include "drm_common.cuh"
 
 namespace drm {
@@ -39,11 +40,24 @@ struct RneaArgs {
     const float* __restrict__ q;
     const float* __restrict__ qd;
     const float* __restrict__ qdd;
-    float* __restrict__ tau;
+    float* __restrict__ tau;             // [B, n] or null (DUMP launches may skip it)
+    float* __restrict__ vels;            // DUMP: [n_links, 6, B] body-frame spatial velocity  (ang 3, lin 3), or null
+    float* __restrict__ accs;            // DUMP: [n_links, 6, B] body-frame spatial acceleration (ang 3, lin 3), or null
+    float* __restrict__ forces;          // DUMP: [n_links, 6, B] accumulated body wrench (ang = torque 3, lin = force 3), or null
     int64_t batch;
     uint32_t flags;
     int32_t aligned;
 };
+
+// natural vector from a canonical one:  x[idx(c)] = sgn(c) x~[c]
+__device__ __forceinline__ V3 rnea_unpermute(V3 xt, int code) {
+    const int a = code < 0 ? -code : code;
+    const float s = code < 0 ? -1.f : 1.f;
+    const float c0 = xt.x, c1 = s * xt.y, c2 = s * xt.z;
+    if (a == 1) return v3(c2, c0, c1);
+    if (a == 2) return v3(c1, c2, c0);
+    return v3(c0, c1, c2);
+}
 
 struct RneaSmemLayout {
     int q, qd, qdd, tau, table, link, slots, total_floats;
@@ -60,7 +74,12 @@ struct RneaSmemLayout {
     }
 };
 
-template <int T, bool PACKED>
+// DUMP additionally writes the per-link state the reference leaves in `_bodies[i].vel / .acc / .force`
+// (robot_model.py:183-193, 262-301), un-permuted to the natural link frames, link-major / component-major (coalesced).
+// (A per-warp pipeline version of this kernel -- persistent grid, no CTA barrier, like fk_tree.cu -- was measured at
+// 10.2 G cfg/s against 11.3 G for this CTA-tile form on the Panda: the kernel is issue-bound and the extra loop /
+// addressing instructions cost more than the barrier stalls they remove.)
+template <int T, bool PACKED, bool DUMP>
 __global__ void __launch_bounds__(T)
 rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
     extern __shared__ __align__(128) float smem[];
@@ -113,6 +132,15 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
         auto stv_s = [](uint32_t a, V3 x) { sts_f32(a, x.x); sts_f32(a + E, x.y); sts_f32(a + 2 * E, x.z); };
         const float g = (args.flags & DRMB200_GRAVITY) ? GRAVITY : 0.f;
         const bool damp = (args.flags & DRMB200_DAMPING) != 0;
+        const int64_t B = args.batch;
+        const int64_t b = tile_start + tid;
+        auto dump6 = [&](float* base, int link, V3 ang, V3 lin) {        // natural link frame, [n_links, 6, B]
+            if (base == nullptr) return;
+            const int code = prog.axis[link];
+            const V3 x = rnea_unpermute(ang, code), y = rnea_unpermute(lin, code);
+            float* o = base + ((int64_t)link * 6) * B + b;
+            o[0] = x.x; o[B] = x.y; o[2 * B] = x.z; o[3 * B] = y.x; o[4 * B] = y.y; o[5 * B] = y.z;
+        };
 
         // ---- pass 1: root -> leaves, motion state + body wrench ------------------------------------
         // Packed FP32x2 arithmetic (drm_common.cuh): the velocity-level and the acceleration-level quantities obey the
@@ -120,6 +148,10 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
         // product with r and spatial-inertia product is one FFMA2 per two scalar FMAs.
         const V3 zero = v3(0.f, 0.f, 0.f);
         V3P W = pk3(zero, zero), V = W;                     // state of the previously processed link
+        if (DUMP) {                                         // the root: zero velocity, base acceleration, wrench accumulator
+            stv_s(a_link, zero); stv_s(a_link + 3 * E, zero);
+            dump6(args.vels, 0, zero, zero); dump6(args.accs, 0, zero, v3(0.f, 0.f, g));
+        }
         for (int i = 1; i < N; ++i) {
             if (PACKED) {
                 const uint32_t row = a_tab + i * (DRMB200_TABLE_STRIDE * 4);
@@ -159,6 +191,7 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
                 al.x = fmaf(w.y, qd_k, al.x); al.y = fmaf(-w.x, qd_k, al.y); al.z += qdd_k;         // + w x (0,0,qd) + (0,0,qdd)
                 a.x = fmaf(v.y, qd_k, a.x); a.y = fmaf(-v.x, qd_k, a.y);                            // + v x (0,0,qd)
                 W = pk3(w, al); V = pk3(v, a);
+                if (DUMP) { dump6(args.vels, i, w, v); dump6(args.accs, i, al, a); }
                 // body wrench (robot_model.py:289-293; spatial_vector_algebra.py:321-338), both lanes at once
                 V3 hl_v, hl_a, ha_v, ha_a;
                 upk3(inertia_lin_p(C.m, C.mc, W, V), hl_v, hl_a);
@@ -209,6 +242,7 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
             v = mulT(M, cross_add(wp, C.r, vp));
             al = mulT(M, alp) + cross_z(w, qd_k); al.z += qdd_k;
             a = mulT(M, cross_add(alp, C.r, ap)) + cross_z(v, qd_k);
+            if (DUMP) { dump6(args.vels, i, w, v); dump6(args.accs, i, al, a); }
             // body wrench (robot_model.py:289-293; spatial_vector_algebra.py:321-338)
             const V3 hl_a = C.m * a - cross(C.mc, al);
             const V3 ha_a = mul_add(C.Io, al, cross(C.mc, a));
@@ -237,6 +271,7 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
             V3 f = ldv_s(lk);
             V3 nn = ldv_s(lk + 3 * E);
             if (i + 1 < N && prog.tip[i] < 0) { f = f + carry_f; nn = nn + carry_n; }
+            if (DUMP) dump6(args.forces, i, nn, f);
             const int c = prog.dof[i];
             const uint32_t row = a_tab + i * (DRMB200_TABLE_STRIDE * 4);
             if (c >= 0) {
@@ -245,7 +280,7 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
                 sts_f32(a_tau + 4u * c, t);
             }
             const int p = prog.parent[i];
-            if (p > 0) {
+            if (p > 0 || (DUMP && p == 0)) {                // the fused kernel never needs the wrench on the root
                 M3 F; V3 r;
                 load_Fr_s(row, F, r);
                 const float cs = lds_f32(lk + 6 * E), sn = lds_f32(lk + 7 * E);
@@ -266,8 +301,10 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
                 }
             }
         }
+        if (DUMP) dump6(args.forces, 0, ldv_s(a_link + 3 * E) + carry_n, ldv_s(a_link) + carry_f);     // link 1 is a child of the root
     }
 
+    if (args.tau == nullptr) return;
     if (bulk) {
         fence_proxy_async();
         __syncthreads();
@@ -333,52 +370,85 @@ int build_tree_program(const drmb200_topology_t* topo, TreeProgram* prog) {
     return DRMB200_OK;
 }
 
-int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
-                            const float* qdd, int64_t batch, uint32_t flags, float* tau, cudaStream_t stream) {
-    TreeProgram prog;
-    int rc = build_tree_program(topo, &prog);
-    if (rc != DRMB200_OK) return rc;
-    if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
-    if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
-    if (table == nullptr || q == nullptr || qd == nullptr || qdd == nullptr || tau == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
-    // tile: 64 for batches that would not fill two waves of 128-row CTAs (more, smaller CTAs balance the SMs and the
-    // shared-memory-limited residency is the same number of warps), and for models whose 128-row footprint is too big
-    int tile = (batch <= 148 * 1024) ? 64 : 128;
-    if ((size_t)RneaSmemLayout(128, prog.n_dofs, prog.n_links, prog.n_slots).total_floats * sizeof(float) > 110 * 1024) tile = 64;
-    const int64_t tiles = (batch + tile - 1) / tile;
-    if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
-
-    RneaArgs args;
-    args.table = table; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
-    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
-
-    const RneaSmemLayout L(tile, prog.n_dofs, prog.n_links, prog.n_slots);
+template <int T, bool PACKED, bool DUMP>
+static int launch_rnea(const TreeProgram& prog, const RneaArgs& args, cudaStream_t stream) {
+    const RneaSmemLayout L(T, prog.n_dofs, prog.n_links, prog.n_slots);
     const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
-    const bool packed = get_option(4) != 0;             // "rnea_packed": FP32x2 arithmetic (default) vs scalar, for A/B runs
-    static size_t configured_by_dev[4][64] = {{0}};
+    const int64_t tiles = (args.batch + T - 1) / T;
+    if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
+    auto kern = rnea_kernel<T, PACKED, DUMP>;
+    static size_t configured_by_dev[64] = {0};     // per instantiation, per device
     int dev = 0;
     cudaGetDevice(&dev);
-    size_t& configured = configured_by_dev[(tile == 64 ? 0 : 1) + (packed ? 2 : 0)][dev & 63];
-    const void* kern = tile == 64 ? (packed ? (const void*)rnea_kernel<64, true> : (const void*)rnea_kernel<64, false>)
-                                  : (packed ? (const void*)rnea_kernel<128, true> : (const void*)rnea_kernel<128, false>);
+    size_t& configured = configured_by_dev[dev & 63];
     if (smem_bytes > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
         configured = smem_bytes;
     }
-    if (tile == 64) {
-        if (packed) rnea_kernel<64, true><<<(unsigned)tiles, 64, smem_bytes, stream>>>(prog, args);
-        else rnea_kernel<64, false><<<(unsigned)tiles, 64, smem_bytes, stream>>>(prog, args);
-    } else {
-        if (packed) rnea_kernel<128, true><<<(unsigned)tiles, 128, smem_bytes, stream>>>(prog, args);
-        else rnea_kernel<128, false><<<(unsigned)tiles, 128, smem_bytes, stream>>>(prog, args);
-    }
+    kern<<<(unsigned)tiles, T, smem_bytes, stream>>>(prog, args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("rnea launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
     return DRMB200_OK;
+}
+
+// the tree program depends only on the topology: keep the last two per thread
+static const TreeProgram* cached_tree_program(const drmb200_topology_t* topo, int* rc_out) {
+    struct Cached { bool valid; drmb200_topology_t topo; TreeProgram prog; };
+    static thread_local Cached cache[2] = {};
+    static thread_local int next = 0;
+    *rc_out = DRMB200_OK;
+    if (topo == nullptr) { set_error("topology is null"); *rc_out = DRMB200_EINVAL; return nullptr; }
+    for (auto& c : cache) if (c.valid && memcmp(&c.topo, topo, sizeof(*topo)) == 0) return &c.prog;
+    Cached& c = cache[next];
+    c.valid = false;
+    *rc_out = build_tree_program(topo, &c.prog);
+    if (*rc_out != DRMB200_OK) return nullptr;
+    c.topo = *topo; c.valid = true;
+    next ^= 1;
+    return &c.prog;
+}
+
+int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                            const float* qdd, int64_t batch, uint32_t flags, float* tau, cudaStream_t stream) {
+    int rc;
+    const TreeProgram* prog = cached_tree_program(topo, &rc);
+    if (prog == nullptr) return rc;
+    if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
+    if (batch == 0 || prog->n_dofs == 0) return DRMB200_OK;
+    if (table == nullptr || q == nullptr || qd == nullptr || qdd == nullptr || tau == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    // tile: 64 for batches that would not fill two waves of 128-row CTAs (more, smaller CTAs balance the SMs and the
+    // shared-memory-limited residency is the same number of warps), and for models whose 128-row footprint is too big
+    int tile = (batch <= 148 * 1024) ? 64 : 128;
+    if ((size_t)RneaSmemLayout(128, prog->n_dofs, prog->n_links, prog->n_slots).total_floats * sizeof(float) > 110 * 1024) tile = 64;
+    RneaArgs args;
+    args.table = table; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
+    args.vels = args.accs = args.forces = nullptr;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
+    const bool packed = get_option(4) != 0;             // "rnea_packed": FP32x2 arithmetic (default) vs scalar, for A/B runs
+    if (tile == 64) return packed ? launch_rnea<64, true, false>(*prog, args, stream) : launch_rnea<64, false, false>(*prog, args, stream);
+    return packed ? launch_rnea<128, true, false>(*prog, args, stream) : launch_rnea<128, false, false>(*prog, args, stream);
+}
+
+// inverse dynamics + the per-link state of the reference's bodies (vel, acc, force), see rnea_kernel<.., DUMP>
+int dynamic_state_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                         const float* qdd, int64_t batch, uint32_t flags, float* tau, float* vels, float* accs,
+                         float* forces, cudaStream_t stream) {
+    int rc;
+    const TreeProgram* prog = cached_tree_program(topo, &rc);
+    if (prog == nullptr) return rc;
+    if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
+    if (batch == 0) return DRMB200_OK;
+    if (table == nullptr || q == nullptr || qd == nullptr || qdd == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    RneaArgs args;
+    args.table = table; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
+    args.vels = vels; args.accs = accs; args.forces = forces;
+    auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
+    return launch_rnea<64, true, true>(*prog, args, stream);
 }
 
 }  // namespace drm

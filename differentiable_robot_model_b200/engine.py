@@ -43,6 +43,9 @@ _SIGNATURES = {
     "drmb200_inverse_dynamics": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                 ctypes.c_void_p]),
+    "drmb200_dynamic_state": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                             ctypes.c_int64, ctypes.c_uint32, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                             ctypes.c_void_p]),
     "drmb200_inverse_dynamics_backward": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                          _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                          _c_float_p, _c_float_p, _c_float_p, _c_float_p,
@@ -62,6 +65,11 @@ _SIGNATURES = {
     "drmb200_build_link_table": (ctypes.c_int, [_c_float_p, ctypes.c_int32, _c_float_p, ctypes.c_void_p]),
     "drmb200_build_link_table_backward": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_int32, _c_float_p,
                                                          ctypes.c_void_p]),
+    "drmb200_build_link_table_fused": (ctypes.c_int, [_c_float_p, _c_float_p, ctypes.c_void_p, ctypes.c_void_p, _c_float_p,
+                                                      ctypes.c_int32, _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "drmb200_build_link_table_fused_backward": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p,
+                                                               ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_float_p,
+                                                               _c_float_p, ctypes.c_void_p]),
     "drmb200_fk_jacobian_host": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, ctypes.c_int32, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p]),
@@ -219,6 +227,21 @@ def kinematic_state_raw(topo, table, q, qd=None, want_poses=True, want_quats=Fal
     return poses, quats, vels
 
 
+def dynamic_state_raw(topo, table, q, qd, qdd, flags, want_tau=True):
+    """Inverse dynamics + per-link (vel, acc, force) blocks [N, 6, B] in one launch (drmb200_dynamic_state)."""
+    _require_cuda(table, q, qd, qdd)
+    q, qd, qdd = q.contiguous(), qd.contiguous(), qdd.contiguous()
+    B, n = q.shape
+    N, dev = topo.n_links, q.device
+    tau = torch.empty((B, n), device=dev, dtype=torch.float32) if want_tau else None
+    vels, accs, forces = (torch.empty((N, 6, B), device=dev, dtype=torch.float32) for _ in range(3))
+    with torch.cuda.device(dev):
+        rc = lib().drmb200_dynamic_state(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B, flags, _ptr(tau),
+                                         _ptr(vels), _ptr(accs), _ptr(forces), _stream())
+    _check(rc, "drmb200_dynamic_state")
+    return tau, vels, accs, forces
+
+
 def fk_jacobian_host(topo, ee_link, device_index, table, q_host, pos, quat, jlin, jang):
     """Host-buffer FK+Jacobian (H2D / kernel / D2H pipelined inside the library)."""
     _require_cuda(table)
@@ -277,6 +300,40 @@ class BuildLinkTableFunction(torch.autograd.Function):
         _check(rc, "drmb200_build_link_table_backward")
         return g_raw
 
+
+
+class FusedTableFunction(torch.autograd.Function):
+    """flat link-parameter vector [P] -> link table [n_links, 28] in ONE launch (drmb200_build_link_table_fused): the
+    per-(link, parameter) parametrisation modules are applied inside the kernel through an index / kind / offset map.
+    Backward: table_grad -> flat_grad, two tiny launches.  One leaf, one AccumulateGrad node, one optimiser tensor."""
+
+    @staticmethod
+    def forward(ctx, flat, const_raw, src, kind, off):
+        _require_cuda(flat, const_raw, off)
+        flat = flat.contiguous()
+        n_links = const_raw.shape[0]
+        raw = torch.empty_like(const_raw)
+        table = torch.empty((n_links, 28), device=flat.device, dtype=torch.float32)
+        with torch.cuda.device(flat.device):
+            rc = lib().drmb200_build_link_table_fused(_ptr(const_raw), _ptr(flat), _ptr(src), _ptr(kind), _ptr(off), n_links,
+                                                      _ptr(raw), _ptr(table), _stream())
+        _check(rc, "drmb200_build_link_table_fused")
+        ctx.save_for_backward(flat, raw, src, kind)
+        return table
+
+    @staticmethod
+    def backward(ctx, g_table):
+        flat, raw, src, kind = ctx.saved_tensors
+        g_table = g_table.contiguous()
+        _require_cuda(g_table)
+        g_flat = torch.empty_like(flat)
+        scratch = torch.empty_like(raw)
+        with torch.cuda.device(flat.device):
+            rc = lib().drmb200_build_link_table_fused_backward(_ptr(raw), _ptr(g_table), _ptr(flat), _ptr(src), _ptr(kind),
+                                                               raw.shape[0], flat.numel(), _ptr(scratch), _ptr(g_flat),
+                                                               _stream())
+        _check(rc, "drmb200_build_link_table_fused_backward")
+        return g_flat, None, None, None, None
 
 
 class FkJacobianFunction(torch.autograd.Function):
@@ -343,6 +400,52 @@ class FkJacobianMultiFunction(torch.autograd.Function):
             if need_q:
                 q_grad += q_grad_e
         return table_grad, q_grad, None, None, None, None, None
+
+
+class AllLinksFkFunction(torch.autograd.Function):
+    """(table, q) -> (pos [N, B, 3], quat [N, B, 4]) of EVERY link: one launch of the all-links kernel forward; the adjoint
+    is the sum of the single-link adjoints (one FK backward launch per link whose outputs received a gradient)."""
+
+    @staticmethod
+    def forward(ctx, table, q, topo):
+        table, q = table.contiguous(), q.contiguous()
+        poses, quats, _ = kinematic_state_raw(topo, table, q, None, want_poses=True, want_quats=True)
+        ctx.save_for_backward(table, q)
+        ctx.topo = topo
+        pos = poses[:, 9:12].transpose(1, 2).contiguous()       # [N, B, 3]
+        quat = quats.transpose(1, 2).contiguous()               # [N, B, 4]
+        return pos, quat
+
+    @staticmethod
+    def backward(ctx, g_pos, g_quat):
+        table, q = ctx.saved_tensors
+        need_table, need_q = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        B, n = q.shape
+        N = ctx.topo.n_links
+        table_grad = torch.zeros_like(table) if need_table else None
+        q_grad = torch.zeros_like(q) if need_q else None
+        ws = _workspace(ctx.topo, B, q.device)
+        # links whose outputs received no gradient are skipped (one host read of N flags)
+        used = torch.zeros(N, dtype=torch.bool, device=q.device)
+        if g_pos is not None:
+            used |= g_pos.reshape(N, -1).ne(0).any(dim=1)
+        if g_quat is not None:
+            used |= g_quat.reshape(N, -1).ne(0).any(dim=1)
+        for link in torch.nonzero(used).flatten().tolist():
+            if link == 0:
+                continue                                         # the root pose is constant
+            gp = None if g_pos is None else g_pos[link].contiguous()
+            gq = None if g_quat is None else g_quat[link].contiguous()
+            _require_cuda(gp, gq)
+            q_grad_l = torch.empty_like(q) if need_q else None
+            with torch.cuda.device(q.device):
+                rc = lib().drmb200_fk_jacobian_backward(ctypes.byref(ctx.topo), int(link), _ptr(table), _ptr(q), B, _ptr(gp),
+                                                        _ptr(gq), None, None, _ptr(q_grad_l), _ptr(table_grad), _ptr(ws),
+                                                        _stream())
+            _check(rc, "drmb200_fk_jacobian_backward")
+            if need_q:
+                q_grad += q_grad_l
+        return table_grad, q_grad, None
 
 
 class InverseDynamicsFunction(torch.autograd.Function):

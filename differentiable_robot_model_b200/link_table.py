@@ -146,6 +146,71 @@ def gather_raw_parameters(bodies, device):
     return const.index_copy(0, index, vals).reshape(len(bodies), RAW_STRIDE)
 
 
+class FusedLinkParameters(torch.nn.Module):
+    """All learnable link parameters of a model in ONE flat ``nn.Parameter`` (BASELINE config 5: 21 modules -> one
+    tensor, one table-build launch, one AccumulateGrad node, one fused optimiser launch).
+
+    Built by ``DifferentiableRobotModel.fuse_learnable_parameters()`` from the parametrisation modules that are
+    installed at that moment.  Supported: ``UnconstrainedScalar`` / ``UnconstrainedTensor`` (identity) and
+    ``PositiveScalar`` (``l^2 + min_val``) -- the ones the reference's examples use
+    (``examples/learn_dynamics_iiwa.py:57-65``); anything else raises and the model stays on the per-module path.
+    The modules' own Parameters are re-pointed at slices of the flat storage, so ``print_learnable_params`` /
+    ``state_dict`` keep showing the live values; only the flat vector receives gradients."""
+
+    def __init__(self, bodies, device):
+        super().__init__()
+        from .rigid_body_params import PositiveScalar, UnconstrainedScalar, UnconstrainedTensor
+        const, learnable, _ = _raw_layout(bodies, device)
+        n_raw = const.numel()
+        src = torch.full((n_raw,), -1, dtype=torch.int32)
+        kind = torch.zeros(n_raw, dtype=torch.int32)
+        off = torch.zeros(n_raw, dtype=torch.float32)
+        chunks, owners, cursor = [], [], 0
+
+        def claim(param, raw_offset, size, k, o, module):
+            nonlocal cursor
+            if param.numel() != size:
+                raise ValueError(f"{type(module).__name__}: {param.numel()} values for a link parameter of {size}")
+            chunks.append(param.detach().reshape(-1).to(dtype=torch.float32, device=device))
+            owners.append((param, cursor))
+            if raw_offset is not None:
+                src[raw_offset:raw_offset + size] = torch.arange(cursor, cursor + size, dtype=torch.int32)
+                kind[raw_offset:raw_offset + size] = k
+                off[raw_offset:raw_offset + size] = o
+            cursor += size
+
+        seen = set()
+        for module, raw_offset, size in learnable:
+            if isinstance(module, PositiveScalar):
+                claim(module.l, raw_offset, size, 1, float(module._min_val), module)
+            elif isinstance(module, (UnconstrainedScalar, UnconstrainedTensor)):
+                claim(module.param, raw_offset, size, 0, 0.0, module)
+            else:
+                raise ValueError(f"cannot fuse a {type(module).__name__} parametrisation (supported: UnconstrainedScalar, "
+                                 "UnconstrainedTensor, PositiveScalar); the model keeps evaluating its modules one by one")
+            seen.add(id(module))
+        # modules on fixed-joint origins feed nothing (reference quirk, rigid_body.py:64-67) but stay parameters
+        for body in bodies:
+            for owner, names in ((body, ("trans", "rot_angles", "joint_damping")), (body.inertia, ("mass", "com", "inertia_mat"))):
+                for name in names:
+                    module = getattr(owner, name)
+                    if isinstance(module, torch.nn.Module) and id(module) not in seen:
+                        for p_ in module.parameters():
+                            claim(p_, None, p_.numel(), 0, 0.0, module)
+        self.flat = torch.nn.Parameter(torch.cat(chunks) if chunks else torch.zeros(0, device=device))
+        self.register_buffer("const_raw", const.reshape(len(bodies), RAW_STRIDE).contiguous(), persistent=False)
+        self.register_buffer("src", src.to(device), persistent=False)
+        self.register_buffer("kind", kind.to(device), persistent=False)
+        self.register_buffer("off", off.to(device), persistent=False)
+        for param, start in owners:                       # the modules' Parameters become views of the flat storage
+            param.data = self.flat.data[start:start + param.numel()].view(param.shape)
+            param.requires_grad_(False)                   # gradients (and optimiser updates) go through `flat` only
+
+    def table(self):
+        from . import engine
+        return engine.FusedTableFunction.apply(self.flat, self.const_raw, self.src, self.kind, self.off)
+
+
 def build_link_table(bodies, device):
     """Evaluate every link's parameter callables into the ``[n_links, 28]`` fp32 device table.
 

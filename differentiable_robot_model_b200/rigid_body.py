@@ -139,6 +139,18 @@ class DifferentiableRigidBody(torch.nn.Module):
         """Body-frame spatial velocity (``SpatialMotionVec``) for the last ``update_kinematic_state`` call."""
         return self._model_ref()._body_vel(self.joint_id)
 
+    @property
+    def acc(self):
+        """Body-frame spatial acceleration (``SpatialMotionVec``; base acceleration = gravity folded in like the
+        reference, ``robot_model.py:262-277``) for the inputs of the last ``compute_inverse_dynamics`` call."""
+        return self._model_ref()._body_acc(self.joint_id)
+
+    @property
+    def force(self):
+        """Wrench of this link plus everything it carries (``SpatialForceVec``, ``robot_model.py:284-301``) for the
+        inputs of the last ``compute_inverse_dynamics`` call."""
+        return self._model_ref()._body_force(self.joint_id)
+
     def get_joint_limits(self):
         return self.joint_limits
 

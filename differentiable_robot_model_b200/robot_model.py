@@ -30,7 +30,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import engine
-from .link_table import build_link_table, compile_topology
+from .link_table import FusedLinkParameters, build_link_table, compile_topology
 from .rigid_body import DifferentiableRigidBody
 from .urdf_utils import URDFRobotModel
 
@@ -169,12 +169,27 @@ class DifferentiableRobotModel(torch.nn.Module):
         the result carries an autograd graph when grad mode is on and a parameter requires grad."""
         if getattr(self, "_shared_table", None) is not None:
             return self._shared_table
+        if getattr(self, "fused_link_params", None) is not None:
+            return self.fused_link_params.table()
         if self._any_learnable_module():
             return build_link_table(self._bodies, self._device)
         if self._table_cache is None:
             with torch.no_grad():
                 self._table_cache = build_link_table(self._bodies, self._device)
         return self._table_cache
+
+    def fuse_learnable_parameters(self) -> torch.nn.Parameter:
+        """Gather every learnable link parameter into ONE flat ``nn.Parameter`` (returned; also
+        ``model.fused_link_params.flat``): the link table is then built from it by one kernel, the backward leaves one
+        gradient tensor and ``torch.optim.Adam(model.parameters(), fused=True)`` updates everything in one launch.  Call
+        after the last ``make_link_param_learnable``; values and gradients are the same as on the per-module path (the
+        modules' own Parameters become views of the flat storage and stop requiring grad).  Raises ``ValueError`` for
+        parametrisations other than UnconstrainedScalar / UnconstrainedTensor / PositiveScalar."""
+        if self._device.type != "cuda":
+            raise RuntimeError("fuse_learnable_parameters needs a CUDA model")
+        self.fused_link_params = None
+        self.fused_link_params = FusedLinkParameters(self._bodies, self._device)
+        return self.fused_link_params.flat
 
     def _kinematic_params_learnable(self) -> bool:
         """True if any joint origin (``trans`` / ``rot_angles`` of a movable link) is a learnable module with a
@@ -187,6 +202,11 @@ class DifferentiableRobotModel(torch.nn.Module):
                 attr = getattr(body, name)
                 if isinstance(attr, torch.nn.Module):
                     params = list(attr.parameters())
+                    fused = getattr(self, "fused_link_params", None)
+                    if fused is not None and params:                            # views of the flat vector
+                        if fused.flat.requires_grad:
+                            return True
+                        continue
                     if not params or any(p.requires_grad for p in params):      # parameter-free modules: be safe
                         return True
         return False
@@ -202,9 +222,10 @@ class DifferentiableRobotModel(torch.nn.Module):
     def _fk_jacobian(self, q, link_name, want_pos, want_quat, want_jac):
         link_idx = self._name_to_idx_map[link_name]          # KeyError for unknown links (robot_model.py:245)
         table = self._link_table()
-        if torch.is_grad_enabled() and (q.requires_grad or table.requires_grad):
+        # kinematics depend on the (F, r) columns only: with nothing but inertial parameters learnable there is no graph
+        if torch.is_grad_enabled() and (q.requires_grad or (table.requires_grad and self._kinematic_params_learnable())):
             return engine.FkJacobianFunction.apply(table, q, self._topology, link_idx, want_pos, want_quat, want_jac)
-        return engine.fk_jacobian_raw(self._topology, link_idx, table, q, want_pos, want_quat, want_jac)
+        return engine.fk_jacobian_raw(self._topology, link_idx, table.detach(), q, want_pos, want_quat, want_jac)
 
     @tensor_check
     def compute_forward_kinematics(
@@ -292,6 +313,7 @@ class DifferentiableRobotModel(torch.nn.Module):
         """
         self._check_q(q, qd, qdd_des)
         flags = (engine.GRAVITY if include_gravity else 0) | (engine.DAMPING if use_damping else 0)
+        self._remember_dynamic_inputs(q, qd, qdd_des, flags)       # for the lazy `_bodies[i].acc / .force`
         table = self._link_table()
         if not self._kinematic_params_learnable():
             flags |= engine.INERTIAL_GRADS_ONLY     # backward hint: only (I_o, mc, m, damping) columns can matter
@@ -390,45 +412,83 @@ class DifferentiableRobotModel(torch.nn.Module):
     @tensor_check
     def update_kinematic_state(self, q: torch.Tensor, qd: torch.Tensor) -> None:
         r"""World pose and body-frame spatial velocity of every link for joint state ``(q, qd)``
-        (``robot_model.py:140-195``), in ONE launch (``csrc/kinematic_state.cu``).  Afterwards
-        ``model._bodies[i].pose`` (a ``CoordinateTransform``) and ``model._bodies[i].vel`` (a ``SpatialMotionVec``)
-        are available like in the reference; they are views of the kernel's link-major output, built on access.
-        This state is NOT differentiable and is only refreshed by this method (the fused FK / RNEA kernels do not
-        write per-link state to HBM)."""
+        (``robot_model.py:140-195``).  Afterwards ``model._bodies[i].pose`` (a ``CoordinateTransform``) and
+        ``model._bodies[i].vel`` (a ``SpatialMotionVec``) are available like in the reference.  The fused FK / RNEA kernels
+        write no per-link state to HBM, so this only RECORDS the joint state; the first access of a body's ``pose`` /
+        ``vel`` runs ONE launch of the all-links kernel (``csrc/kinematic_state.cu``) and later accesses are views of its
+        link-major output.  ``compute_inverse_dynamics`` records its ``(q, qd)`` the same way (the reference updates the
+        kinematic state as a side effect there, ``robot_model.py:335``).  This state is not differentiable."""
         self._check_q(q, qd)
-        with torch.no_grad():
-            poses, _, vels = engine.kinematic_state_raw(self._topology, self._link_table().detach(), q, qd)
-        self._kin_state = (poses, vels)
+        self._kin_inputs = (q.detach(), qd.detach())
+        self._kin_state = None
         return
+
+    def _kinematic_state(self):
+        if getattr(self, "_kin_state", None) is None:
+            inputs = getattr(self, "_kin_inputs", None)
+            if inputs is None:
+                raise RuntimeError("no kinematic state: call update_kinematic_state(q, qd) first")
+            with torch.no_grad():
+                poses, _, vels = engine.kinematic_state_raw(self._topology, self._link_table().detach(), *inputs)
+            self._kin_state = (poses, vels)
+        return self._kin_state
 
     def _body_pose(self, i):
         from .spatial_vector_algebra import CoordinateTransform
-        state = getattr(self, "_kin_state", None)
-        if state is None:
-            raise RuntimeError("no kinematic state: call update_kinematic_state(q, qd) first")
-        block = state[0][i]                                       # [12, B]
+        block = self._kinematic_state()[0][i]                     # [12, B]
         return CoordinateTransform(rot=block[:9].t().reshape(-1, 3, 3), trans=block[9:12].t().contiguous(),
                                    device=self._device)
 
     def _body_vel(self, i):
         from .spatial_vector_algebra import SpatialMotionVec
-        state = getattr(self, "_kin_state", None)
-        if state is None:
-            raise RuntimeError("no kinematic state: call update_kinematic_state(q, qd) first")
-        block = state[1][i]                                       # [6, B]: ang, lin
+        block = self._kinematic_state()[1][i]                     # [6, B]: ang, lin
         return SpatialMotionVec(lin_motion=block[3:6].t().contiguous(), ang_motion=block[0:3].t().contiguous())
 
     @tensor_check
     def compute_forward_kinematics_all_links(self, q: torch.Tensor) -> Dict[str, Tuple[torch.Tensor, torch.Tensor]]:
         r"""``{link_name: (pos, quat)}`` for every link (``robot_model.py:198-221``) from ONE launch of the all-links
-        kernel (not differentiable; use ``compute_forward_kinematics`` per link when gradients are needed).
+        kernel.  Differentiable w.r.t. ``q`` and every learnable link parameter, like the reference's recursion (the
+        adjoint runs the single-link FK backward kernel once per link that received a gradient).
         Like the reference, 1-D inputs give un-squeezed ``[1, .]`` values (the dict bypasses the squeeze)."""
         self._check_q(q)
-        with torch.no_grad():
-            poses, quats, _ = engine.kinematic_state_raw(self._topology, self._link_table().detach(), q, None,
-                                                         want_poses=True, want_quats=True)
-        return {name: (poses[i, 9:12].t().contiguous(), quats[i].t().contiguous())
-                for i, name in enumerate(self.get_link_names())}
+        table = self._link_table()
+        if torch.is_grad_enabled() and (q.requires_grad or table.requires_grad):
+            pos, quat = engine.AllLinksFkFunction.apply(table, q, self._topology)
+        else:
+            poses, quats, _ = engine.kinematic_state_raw(self._topology, table, q, None, want_poses=True, want_quats=True)
+            pos, quat = poses[:, 9:12].transpose(1, 2), quats.transpose(1, 2)
+        return {name: (pos[i].contiguous(), quat[i].contiguous()) for i, name in enumerate(self.get_link_names())}
+
+    # per-body dynamic state (reference: `_bodies[i].acc / .force` after compute_inverse_dynamics, robot_model.py:262-301)
+    def _remember_dynamic_inputs(self, q, qd, qdd, flags):
+        self._dyn_inputs = (q.detach(), qd.detach(), qdd.detach(), flags & (engine.GRAVITY | engine.DAMPING))
+        self._dyn_state = None
+        self._kin_inputs = (q.detach(), qd.detach())               # robot_model.py:335: update_kinematic_state(q, qd)
+        self._kin_state = None
+
+    def _dynamic_state(self):
+        """(vels, accs, forces) blocks [N, 6, B] for the inputs of the last compute_inverse_dynamics call: ONE launch of
+        the dump variant of the RNEA kernel, issued on first access (the fused kernel itself writes no per-link state)."""
+        if getattr(self, "_dyn_state", None) is None:
+            inputs = getattr(self, "_dyn_inputs", None)
+            if inputs is None:
+                raise RuntimeError("no dynamic state: call compute_inverse_dynamics(q, qd, qdd) first")
+            q, qd, qdd, flags = inputs
+            with torch.no_grad():
+                _, vels, accs, forces = engine.dynamic_state_raw(self._topology, self._link_table().detach(), q, qd, qdd,
+                                                                 flags, want_tau=False)
+            self._dyn_state = (vels, accs, forces)
+        return self._dyn_state
+
+    def _body_acc(self, i):
+        from .spatial_vector_algebra import SpatialMotionVec
+        block = self._dynamic_state()[1][i]                      # [6, B]: ang, lin
+        return SpatialMotionVec(lin_motion=block[3:6].t().contiguous(), ang_motion=block[0:3].t().contiguous())
+
+    def _body_force(self, i):
+        from .spatial_vector_algebra import SpatialForceVec
+        block = self._dynamic_state()[2][i]                      # [6, B]: torque, force
+        return SpatialForceVec(lin_force=block[3:6].t().contiguous(), ang_force=block[0:3].t().contiguous())
 
     # ------------------------------------------------------------------------------------------
     # learnable link parameters (robot_model.py:669-713)
@@ -448,6 +508,8 @@ class DifferentiableRobotModel(torch.nn.Module):
         owner = self._get_parent_object_of_param(link_name, parameter_name)
         owner.__delattr__(parameter_name)
         owner.add_module(parameter_name, parametrization.to(self._device))
+        if getattr(self, "fused_link_params", None) is not None:
+            raise RuntimeError("make_link_param_learnable after fuse_learnable_parameters(): fuse once, after the last one")
         self.invalidate_link_table()
 
     def _learnable_module(self, link_name: str, parameter_name: str):

@@ -151,6 +151,21 @@ int drmb200_inverse_dynamics(const drmb200_topology_t* topo,
                              int64_t batch, uint32_t flags, float* tau, void* cuda_stream);
 
 /*
+ * Inverse dynamics PLUS the per-link state the reference leaves behind in its body objects after
+ * compute_inverse_dynamics (robot_model.py:183-193 `vel`, :262-277 `acc`, :284-301 `force`), in one launch.  Link-major,
+ * component-major blocks (coalesced stores), natural link frames, row order (angular 3, linear 3):
+ *   vels   [n_links, 6, B]  body-frame spatial velocity            (SpatialMotionVec .ang, .lin)
+ *   accs   [n_links, 6, B]  body-frame spatial acceleration, base acceleration (0, 0, 9.81) folded in when GRAVITY is set
+ *   forces [n_links, 6, B]  wrench of the link plus everything it carries (SpatialForceVec .ang = torque, .lin = force);
+ *                           row 0 is the wrench transmitted to the root
+ * Any of tau / vels / accs / forces may be NULL.
+ */
+int drmb200_dynamic_state(const drmb200_topology_t* topo,
+                          const float* table, const float* q, const float* qd, const float* qdd,
+                          int64_t batch, uint32_t flags, float* tau, float* vels, float* accs, float* forces,
+                          void* cuda_stream);
+
+/*
  * Adjoint of drmb200_inverse_dynamics given g_tau [B, n_dofs].  Any of q_grad / qd_grad / qdd_grad
  * [B, n_dofs] and table_grad [n_links, 28] may be NULL.
  */
@@ -218,6 +233,20 @@ int drmb200_kinematic_state(const drmb200_topology_t* topo, const float* table, 
 int drmb200_build_link_table(const float* raw, int32_t n_links, float* table, void* cuda_stream);
 int drmb200_build_link_table_backward(const float* raw, const float* table_grad, int32_t n_links,
                                       float* raw_grad, void* cuda_stream);
+
+/*
+ * Fused parametrisation (BASELINE config 5): every learnable entry of the raw block is a function of ONE flat device vector,
+ *   raw[k] = const_raw[k] (src[k] < 0) | flat[src[k]] (kind[k] == 0) | flat[src[k]]^2 + off[k] (kind[k] == 1),
+ * which covers the reference's UnconstrainedScalar / UnconstrainedTensor / PositiveScalar modules
+ * (rigid_body_params.py:14-56).  Forward: one launch (raw rows are written to raw_out for the backward, then the table as
+ * above).  Backward: table_grad -> flat_grad [n_flat] (two tiny launches; raw_grad_scratch [n_links, 20] is workspace).
+ * All pointers are device pointers; src / kind / off have n_links * DRMB200_RAW_STRIDE entries.
+ */
+int drmb200_build_link_table_fused(const float* const_raw, const float* flat, const int32_t* src, const int32_t* kind,
+                                   const float* off, int32_t n_links, float* raw_out, float* table, void* cuda_stream);
+int drmb200_build_link_table_fused_backward(const float* raw, const float* table_grad, const float* flat,
+                                            const int32_t* src, const int32_t* kind, int32_t n_links, int32_t n_flat,
+                                            float* raw_grad_scratch, float* flat_grad, void* cuda_stream);
 
 /*
  * Host-buffer variant of drmb200_fk_jacobian: q and the outputs are HOST pointers (pinned memory

@@ -281,8 +281,9 @@ def bench_backward_kernels(batch):
     return out
 
 
-def bench_train_step(batch):
-    """config 5 on one shard: FK+Jacobian + RNEA forward, scalar loss, backward to 21 inertial tensors."""
+def bench_train_step(batch, fused=False):
+    """config 5 on one shard: FK+Jacobian + RNEA forward, scalar loss, backward to 21 inertial tensors.
+    fused: model.fuse_learnable_parameters() (one flat Parameter, one table launch) + Adam(fused=True)."""
     m = drm.DifferentiableKUKAiiwa(device=DEV)
     for i in range(1, 8):
         b = m._bodies[i]
@@ -290,6 +291,8 @@ def bench_train_step(batch):
         m.make_link_param_learnable(b.name, "com", UnconstrainedTensor(1, 3, init_tensor=b.inertia.com().detach().clone()))
         m.make_link_param_learnable(b.name, "inertia_mat", UnconstrainedTensor(
             3, 3, init_tensor=b.inertia.inertia_mat().detach().clone().reshape(3, 3)))
+    if fused:
+        m.fuse_learnable_parameters()
     robot = O.load_robot(m.urdf_path, torch.float32)
     q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, batch, seed=0))
     target = torch.randn(batch, 7, device=DEV)
@@ -304,14 +307,14 @@ def bench_train_step(batch):
         loss.backward()
 
     ms = timed(step, 20)
-    res = {"batch": batch, "ms_fwd_bwd": ms, "configs_per_s": batch / ms * 1e3,
+    res = {"batch": batch, "fused_parameters": fused, "ms_fwd_bwd": ms, "configs_per_s": batch / ms * 1e3,
            "algorithmic_bytes_per_config": 420, "achieved_GBps": batch * 420 / ms / 1e6,
            "note": "includes the differentiable table build (~40 small torch kernels) and the torch loss ops"}
 
     # the same step (plus the Adam update) captured ONCE in a CUDA graph and replayed: the host-side autograd / module
     # overhead that dominates the eager step disappears, what remains is the kernels
     try:
-        opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True, fused=fused)
 
         def full_step():
             opt.zero_grad(set_to_none=False)
@@ -352,6 +355,16 @@ def bench_train_step(batch):
 
 def main():
     out = {"peak_GBps": PEAK, "gpu": torch.cuda.get_device_name(0)}
+    if os.environ.get("BENCH_ONLY") == "config5":
+        out["config5_kuka_train_step"] = [bench_train_step(131072, fused=False), bench_train_step(131072, fused=True)]
+        print(json.dumps(out))
+        return
+    if os.environ.get("BENCH_ONLY") == "rnea":
+        os.environ["DRMB200_SKIP_CPU"] = "1"
+        out["config3_panda_rnea"] = [bench_rnea(drm.DifferentiableFrankaPanda, b) for b in (65536, 1 << 21)]
+        out["kuka_rnea"] = [bench_rnea(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 21)]
+        print(json.dumps(out))
+        return
     if os.environ.get("BENCH_ONLY") == "config4":
         allegro = drm.DifferentiableRobotModel(os.path.join(drm.robot_model.robot_description_folder,
                                                             "allegro/urdf/allegro_hand_description_left.urdf"), device=DEV)
@@ -375,7 +388,7 @@ def main():
     tips = ["link_3.0_tip", "link_7.0_tip", "link_11.0_tip", "link_15.0_tip"]
     out["config4_allegro_fk_jac_tree_kernel_one_tip"] = [bench_fk_multi(allegro, tips[3:], b) for b in (32768, 1 << 21)]
     out["config4_allegro_fk_jac_fused_4_tips"] = [bench_fk_multi(allegro, tips, b) for b in (32768, 1 << 20)]
-    out["config5_kuka_train_step"] = [bench_train_step(b) for b in (131072,)]
+    out["config5_kuka_train_step"] = [bench_train_step(131072, fused=False), bench_train_step(131072, fused=True)]
     out["kuka_backward_kernels"] = [bench_backward_kernels(131072)]
     out["kuka_mass_matrix"] = [bench_mass_matrix(drm.DifferentiableKUKAiiwa, b) for b in (65536, 1 << 20)]
     out["kuka_kinematic_state"] = [bench_kinematic_state(drm.DifferentiableKUKAiiwa, 1 << 20)]

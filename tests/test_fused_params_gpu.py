@@ -1,0 +1,90 @@
+"""GPU: all learnable link parameters fused into one flat Parameter (model.fuse_learnable_parameters): the table, the
+gradients and a few optimiser steps must equal the per-module path (the reference's mechanism, robot_model.py:682-689)."""
+import copy
+
+import pytest
+import torch
+
+from conftest import assert_close, urdf_path
+import differentiable_robot_model_b200 as drm
+from differentiable_robot_model_b200 import engine
+from differentiable_robot_model_b200.rigid_body_params import (CovParameterized3DInertiaMatrixNet, PositiveScalar,
+                                                                UnconstrainedScalar, UnconstrainedTensor)
+from oracle import drm_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def learnable_kuka(kinematic):
+    torch.manual_seed(0)
+    m = drm.DifferentiableKUKAiiwa(device=DEV)
+    for i in range(1, 8):
+        b = m._bodies[i]
+        m.make_link_param_learnable(b.name, "mass", PositiveScalar(init_param=b.inertia.mass().detach().clone().cpu() * 1.1))
+        m.make_link_param_learnable(b.name, "com", UnconstrainedTensor(1, 3, init_tensor=b.inertia.com().detach().clone() + 0.01))
+        m.make_link_param_learnable(b.name, "inertia_mat", UnconstrainedTensor(3, 3, init_tensor=b.inertia.inertia_mat().detach().clone().reshape(3, 3)))
+    m.make_link_param_learnable("iiwa_link_3", "joint_damping", UnconstrainedScalar(init_val=torch.tensor([0.3])))
+    if kinematic:
+        m.make_link_param_learnable("iiwa_link_2", "trans", UnconstrainedTensor(1, 3, init_tensor=m._bodies[2].trans().detach().clone()))
+        m.make_link_param_learnable("iiwa_link_ee", "trans", UnconstrainedTensor(1, 3))       # fixed joint: frozen in the table
+    return m
+
+
+@pytest.mark.parametrize("kinematic", [False, True])
+def test_fused_equals_per_module_path(kinematic):
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float32)
+    q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, 2048, seed=1))
+    target = torch.randn(2048, 7, generator=torch.Generator().manual_seed(2)).to(DEV)
+
+    def loss_of(m):
+        tau = m.compute_inverse_dynamics(q, qd, qdd)
+        pos, _ = m.compute_forward_kinematics(q, "iiwa_link_ee")
+        return (tau - target).square().mean() + pos.square().mean()
+
+    plain, fused = learnable_kuka(kinematic), learnable_kuka(kinematic)
+    names = [n for n, _ in plain.named_parameters()]
+    flat = fused.fuse_learnable_parameters()
+    assert flat.numel() == sum(p.numel() for p in plain.parameters())
+    assert torch.equal(plain._link_table().detach(), fused._link_table().detach())
+    base = engine.launch_count()
+    fused._link_table()
+    assert engine.launch_count() - base == 1                       # ONE launch: parameters -> table
+
+    opt_p = torch.optim.Adam(plain.parameters(), lr=1e-2)
+    opt_f = torch.optim.Adam(fused.parameters(), lr=1e-2, fused=True)
+    for step in range(3):
+        opt_p.zero_grad(); opt_f.zero_grad()
+        lp, lf = loss_of(plain), loss_of(fused)
+        assert_close(lf.item(), lp.item(), rtol=1e-6, atol=1e-7, what=f"loss step {step}")
+        lp.backward(); lf.backward()
+        # gradient of the flat vector == the per-module gradients, in module order
+        per_module = {n: p.grad for n, p in plain.named_parameters()}
+        got = {}
+        for n, p in fused.named_parameters():
+            if n == "fused_link_params.flat":
+                continue
+            start = (p.data_ptr() - flat.data_ptr()) // 4
+            got[n] = flat.grad[start:start + p.numel()].view(p.shape)
+        for n in names:
+            want = per_module[n]
+            want = torch.zeros_like(got[n]) if want is None else want
+            scale = max(1.0, float(want.abs().max()))
+            assert_close(got[n].cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol=1e-6 * scale, what=f"grad {n} step {step}")
+        opt_p.step(); opt_f.step()
+    for (n, a), (_, b) in zip(plain.named_parameters(), ((n, p) for n, p in fused.named_parameters() if n != "fused_link_params.flat")):
+        assert_close(b.detach().cpu().numpy(), a.detach().cpu().numpy(), rtol=1e-5, atol=1e-6, what=f"param {n} after 3 steps")
+
+
+def test_unsupported_parametrisation_is_rejected_and_model_keeps_working():
+    m = drm.DifferentiableKUKAiiwa(device=DEV)
+    m.make_link_param_learnable("iiwa_link_1", "inertia_mat", CovParameterized3DInertiaMatrixNet())
+    with pytest.raises(ValueError, match="cannot fuse"):
+        m.fuse_learnable_parameters()
+    q = torch.zeros(4, 7, device=DEV)
+    assert torch.isfinite(m.compute_inverse_dynamics(q, q, q)).all()
+    with pytest.raises(RuntimeError, match="after fuse"):
+        f = drm.DifferentiableKUKAiiwa(device=DEV)
+        f.make_link_param_learnable("iiwa_link_1", "mass", PositiveScalar())
+        f.fuse_learnable_parameters()
+        f.make_link_param_learnable("iiwa_link_2", "mass", PositiveScalar())
