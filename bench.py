@@ -280,6 +280,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-large", action="store_true")
     ap.add_argument("--no-modes", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded BASELINE configs 4 and 5 (scripts/bench_sharded.py)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -494,6 +495,30 @@ def main():
         del q_big, out_big
         torch.cuda.empty_cache()
         engine.set_option("fk_pdl", 2)
+
+    # ---- the sharded BASELINE configs (4: Allegro fingertips, 5: Kuka training step) on this rank's shard --------
+    if not args.no_sharded:
+        try:
+            sys.path.insert(0, os.path.join(REPO, "scripts"))
+            import bench_sharded
+            peak_gbs = peak
+            c4 = bench_sharded.config4(dev, rank, barrier)
+            c5 = bench_sharded.config5(dev, rank, world, dist if world > 1 else None, barrier)
+            t4f, t4p, t5 = (job_ms([c4["fused_ms_per_step"]]), job_ms([c4["per_tip_ms_per_step"]]), job_ms([c5["ms_per_step"]]))
+            b4, b5 = c4["per_gpu_batch"], c5["per_gpu_batch"]
+            result["sharded_configs"] = {
+                "config4_allegro_fk_jac_4_fingertips": {
+                    "global_batch": b4 * world, "per_gpu_batch": b4, "fused_launch_ms_per_step": t4f,
+                    "fused_configs_per_s": world * b4 / (t4f * 1e-3),
+                    "fused_hbm_frac_per_gpu": b4 * c4["algorithmic_bytes_per_config"] / (t4f * 1e-3) / 1e9 / peak_gbs,
+                    "four_single_tip_launches_ms_per_step": t4p, "four_single_tip_configs_per_s": world * b4 / (t4p * 1e-3),
+                    "collective": "none (batch-sharded)"},
+                "config5_kuka_fk_jac_rnea_backward_adam": {
+                    "global_batch": b5 * world, "per_gpu_batch": b5, "ms_per_step": t5, "configs_per_s": world * b5 / (t5 * 1e-3),
+                    "allreduce_scalars_per_step": c5["allreduce_scalars"], "step": c5["step"], "final_loss_rank0": c5["final_loss"]},
+                "timing": "median over repetitions per rank, max over ranks; weak scaling (fixed per-GPU shard)"}
+        except Exception as exc:                              # report, do not hide
+            result["sharded_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- end to end through the host-buffer C-ABI call ---------------------------------------------
     if not args.no_e2e:

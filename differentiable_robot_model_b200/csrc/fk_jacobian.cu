@@ -524,26 +524,21 @@ static int launch_fk_t(int tile, bool with_jac, const PathProgram& prog, const F
 // predecessor has started, and a started CTA keeps its shared memory until its own predecessor grid has completed, so the
 // grids ahead of a launch that are not yet complete are all fully resident -- at most 1 / f of them, f = the share of the
 // GPU's shared memory one grid takes.  The library therefore (a) uses mode 2 only for launches with f >= 1/4 and (b) keeps
-// the output ranges of the last 8 FK launches per (device, stream) and falls back to an ordinary launch whenever an input
+// the output ranges of the last 8 FK / multi-link FK launches per (device, stream) and falls back to an ordinary launch whenever an input
 // of the new launch overlaps one of them.  Writes need no check: every launch waits for its predecessor before writing.
-struct Range { uintptr_t lo, hi; };
-struct StreamLog { int dev; cudaStream_t stream; bool used; int head; Range out[8][4]; };
+struct StreamLog { int dev; cudaStream_t stream; bool used; int head; PdlRange out[8][4]; };
 static StreamLog g_logs[16];
 static std::mutex g_log_mu;
 static int g_log_clock = 0;
 
-static bool overlaps(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
+static bool overlaps(const PdlRange& a, const PdlRange& b) { return a.lo < b.hi && b.lo < a.hi; }
 
-static int pdl_mode_for_launch(const PathProgram& prog, const FkArgs& args, int n_links, cudaStream_t stream) {
+// mode the launch may use (0 or the requested one) + log its output ranges; smem_share = f above
+int pdl_decide(cudaStream_t stream, const PdlRange* ins, int n_ins, const PdlRange outs[4], double smem_share) {
     int mode = get_option(7);
     if (mode < 0 || mode > 2) mode = 0;
     int dev = 0;
     cudaGetDevice(&dev);
-    const int n = prog.n_dofs;
-    const uintptr_t B = (uintptr_t)args.batch;
-    auto range = [](const void* p, uintptr_t bytes) { Range r; r.lo = (uintptr_t)p; r.hi = p ? (uintptr_t)p + bytes : 0; return r; };
-    const Range outs[4] = {range(args.pos, B * 12), range(args.quat, B * 16), range(args.jlin, B * 12 * n), range(args.jang, B * 12 * n)};
-    const Range ins[2] = {range(args.q, B * 4 * n), range(args.table, (uintptr_t)n_links * DRMB200_TABLE_STRIDE * 4)};
     std::lock_guard<std::mutex> lock(g_log_mu);
     StreamLog* log = nullptr;
     for (auto& l : g_logs) if (l.used && l.dev == dev && l.stream == stream) { log = &l; break; }
@@ -553,17 +548,26 @@ static int pdl_mode_for_launch(const PathProgram& prog, const FkArgs& args, int 
         log->used = true; log->dev = dev; log->stream = stream;
     }
     if (mode == 2) {
-        // share of the GPU's shared memory this grid takes (the residency bound above)
-        const double smem_per_config = 4.0 * (n + 7 + (args.jlin ? 6 * n : 0));
-        const double f = smem_per_config * (double)args.batch / (148.0 * 227.0 * 1024.0);
-        if (f < 0.25) mode = 0;
+        if (smem_share < 0.25) mode = 0;
         for (int k = 0; k < 8 && mode == 2; ++k)
             for (int o = 0; o < 4 && mode == 2; ++o)
-                if (overlaps(log->out[k][o], ins[0]) || overlaps(log->out[k][o], ins[1])) mode = 0;
+                for (int i = 0; i < n_ins && mode == 2; ++i)
+                    if (overlaps(log->out[k][o], ins[i])) mode = 0;
     }
     for (int o = 0; o < 4; ++o) log->out[log->head][o] = outs[o];
     log->head = (log->head + 1) & 7;
     return mode;
+}
+
+static int pdl_mode_for_launch(const PathProgram& prog, const FkArgs& args, int n_links, cudaStream_t stream) {
+    const int n = prog.n_dofs;
+    const uintptr_t B = (uintptr_t)args.batch;
+    const PdlRange outs[4] = {pdl_range(args.pos, B * 12), pdl_range(args.quat, B * 16), pdl_range(args.jlin, B * 12 * n),
+                              pdl_range(args.jang, B * 12 * n)};
+    const PdlRange ins[2] = {pdl_range(args.q, B * 4 * n), pdl_range(args.table, (uintptr_t)n_links * DRMB200_TABLE_STRIDE * 4)};
+    // share of the GPU's shared memory this grid takes (the residency bound above)
+    const double smem_per_config = 4.0 * (n + 7 + (args.jlin ? 6 * n : 0));
+    return pdl_decide(stream, ins, 2, outs, smem_per_config * (double)args.batch / (148.0 * 227.0 * 1024.0));
 }
 
 int fk_jacobian_device(const drmb200_topology_t* topo, int32_t ee_link, const float* table, const float* q,

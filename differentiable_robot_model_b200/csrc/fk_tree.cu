@@ -60,6 +60,7 @@ struct MtArgs {
     int64_t batch;
     int32_t aligned;
     int32_t use_bulk;
+    int32_t pdl;                          // programmatic dependent launch: 0 off, 2 wait for the predecessor before the first global write
     int32_t nbuf;                         // output tiles per warp: 2 = the next end effector fills one tile while the TMA unit
                                           // drains the other, 1 = half the shared memory, the warp waits for the drain
 };
@@ -105,6 +106,8 @@ fk_tree_kernel(const __grid_constant__ MultiProgram prog, const MtArgs args) {
     const int64_t B = args.batch;
 
     // ---- prologue ------------------------------------------------------------------------------
+    if (args.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // see "fk_pdl" (drm_b200.h)
+    bool waited = args.pdl != 2;                         // pdl 2: wait for the predecessor grid before the first global write
     if (lane == 0) {
         mbar_init(&mbar[2 * warp], 1);
         mbar_init(&mbar[2 * warp + 1], 1);
@@ -253,6 +256,7 @@ fk_tree_kernel(const __grid_constant__ MultiProgram prog, const MtArgs args) {
                 fence_proxy_async();                     // generic-proxy smem writes -> visible to the async proxy
                 __syncwarp();
                 if (lane == 0) {
+                    if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
                     if (args.pos != nullptr) bulk_s2g(args.pos + r * 3, o_pos, (uint32_t)valid * 12u);
                     if (args.quat != nullptr) bulk_s2g(args.quat + r * 4, o_quat, (uint32_t)valid * 16u);
                     if (WITH_JAC) {
@@ -263,6 +267,7 @@ fk_tree_kernel(const __grid_constant__ MultiProgram prog, const MtArgs args) {
                 }
             } else {
                 __syncwarp();
+                if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
                 if (args.pos != nullptr) mt_warp_copy(args.pos + r * 3, o_pos, valid * 3, vec_ok, lane);
                 if (args.quat != nullptr) mt_warp_copy(args.quat + r * 4, o_quat, valid * 4, vec_ok, lane);
                 if (WITH_JAC) {
@@ -271,6 +276,7 @@ fk_tree_kernel(const __grid_constant__ MultiProgram prog, const MtArgs args) {
                 }
                 __syncwarp();
             }
+            waited = true;
         };
 
         for (int i = 0; i < prog.n_root_ee; ++i) emit(prog.root_ee[i], 0);      // the root itself: identity, zero columns
@@ -456,8 +462,27 @@ static int launch_fk_tree(const MultiProgram& prog, const MtArgs& args, cudaStre
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
         configured = smem_bytes;
     }
-    kern<<<(unsigned)ctas, 32 * warps, smem_bytes, stream>>>(prog, args);
-    cudaError_t e = cudaGetLastError();
+    MtArgs largs = args;
+    if (args.pdl < 0) {                                   // decide: hazards against the FK launches in flight, residency share
+        const uintptr_t Bn = (uintptr_t)args.batch * (uintptr_t)prog.n_ee, n = (uintptr_t)prog.n_dofs;
+        const PdlRange outs[4] = {pdl_range(args.pos, Bn * 12), pdl_range(args.quat, Bn * 16), pdl_range(args.jlin, Bn * 12 * n),
+                                  pdl_range(args.jang, Bn * 12 * n)};
+        const PdlRange ins[2] = {pdl_range(args.q, (uintptr_t)args.batch * 4 * n),
+                                 pdl_range(args.table, (uintptr_t)DRMB200_MAX_LINKS * DRMB200_TABLE_STRIDE * 4)};
+        const int mode = pdl_decide(stream, ins, 2, outs, (double)ctas * (double)smem_bytes / (148.0 * 227.0 * 1024.0));
+        largs.pdl = mode == 2 ? 2 : 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(32u * warps);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = largs.pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, prog, largs);
     if (e != cudaSuccess) { set_error("fk_tree launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
     return DRMB200_OK;
@@ -500,6 +525,7 @@ int fk_jacobian_multi_device(const drmb200_topology_t* topo, int32_t n_ee, const
     args.aligned = (al16(q) && al16(pos) && al16(quat) && al16(jlin) && al16(jang) && (n_ee == 1 || (batch & 3) == 0)) ? 1 : 0;
     args.use_bulk = get_option(0) != 0;
     args.nbuf = get_option(10) == 2 ? 2 : 1;
+    args.pdl = -1;                                        // decided at launch (pdl_decide)
     const bool with_jac = jlin != nullptr;
     const int n = prog.n_dofs;
     if (n > 64) { set_error("n_dofs=%d > 64", n); return DRMB200_ELIMIT; }

@@ -1,0 +1,161 @@
+#!/usr/bin/env python
+"""The two SHARDED BASELINE configs on this rank's shard (called by bench.py on every rank; also runnable alone on 1 GPU):
+
+  config 4  Allegro hand FK + Jacobian of the four fingertips, 262 144 configurations over 8 GPUs = 32 768 per GPU:
+            one fused tree-walk launch per step (and, beside it, four single-fingertip launches)
+  config 5  Kuka iiwa FK+Jacobian + RNEA forward, scalar loss, backward to the inertial parameters of links 1..7
+            (21 tensors fused into one flat Parameter), SUM all-reduce of that gradient over the ranks (the only
+            collective of the data path), fused Adam step; 1 048 576 over 8 GPUs = 131 072 per GPU
+
+Timing: CUDA events on the launching stream, `reps` repetitions of a `steps`-step region, median per rank; the caller
+takes the max over ranks.  Weak scaling: the per-GPU shard is fixed."""
+import os
+import statistics
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import differentiable_robot_model_b200 as drm  # noqa: E402
+from differentiable_robot_model_b200 import engine  # noqa: E402
+from differentiable_robot_model_b200.rigid_body_params import UnconstrainedScalar, UnconstrainedTensor  # noqa: E402
+
+ALLEGRO = "allegro/urdf/allegro_hand_description_left.urdf"
+TIPS = ["link_3.0_tip", "link_7.0_tip", "link_11.0_tip", "link_15.0_tip"]
+
+
+def sample(model, batch, seed, dev):
+    gen = torch.Generator().manual_seed(seed)
+    lim = model.get_joint_limits()
+    lo = torch.tensor([float(l["lower"]) for l in lim]); hi = torch.tensor([float(l["upper"]) for l in lim])
+    vel = torch.tensor([float(l["velocity"]) for l in lim])
+    u = torch.rand(3, batch, len(lim), generator=gen)
+    return ((lo + (hi - lo) * u[0]).to(dev), ((2 * u[1] - 1) * 0.2 * vel).to(dev), ((2 * u[2] - 1) * 0.4 * vel).to(dev))
+
+
+def _median_region_ms(stream, replay, reps, barrier):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    out = []
+    for _ in range(reps):
+        barrier()
+        torch.cuda._sleep(400_000)
+        e0.record(stream)
+        replay()
+        e1.record(stream)
+        stream.synchronize()
+        out.append(e0.elapsed_time(e1))
+    return statistics.median(out)
+
+
+def config4(dev, rank, barrier, per_gpu=32768, steps=64, reps=5):
+    """-> {fused_ms_per_step, per_tip_ms_per_step (4 launches)} on this rank's shard."""
+    m = drm.DifferentiableRobotModel(os.path.join(drm.robot_model.robot_description_folder, ALLEGRO), "allegro", device=dev)
+    table, topo = m._link_table(), m._topology
+    ees = [m._name_to_idx_map[t] for t in TIPS]
+    n = m._n_dofs
+    R = 6                                                  # 6 x 56 MB of outputs > L2
+    qs = [sample(m, per_gpu, 100 * rank + r, dev)[0] for r in range(R)]
+    outs = [(torch.empty(4, per_gpu, 3, device=dev), torch.empty(4, per_gpu, 4, device=dev), torch.empty(4, per_gpu, 3, n, device=dev),
+             torch.empty(4, per_gpu, 3, n, device=dev)) for _ in range(R)]
+    stream = torch.cuda.Stream(device=dev)
+    res = {}
+    engine.set_option("fk_pdl", 2)                         # stream of independent batches: launches overlap (drm_b200.h "fk_pdl")
+    with torch.cuda.stream(stream):
+        for name in ("fused", "per_tip"):
+            def step(i):
+                if name == "fused":
+                    engine.fk_jacobian_multi_raw(topo, ees, table, qs[i % R], out=outs[i % R])
+                else:
+                    o = outs[i % R]
+                    for e, ee in enumerate(ees):
+                        engine.fk_jacobian_raw(topo, ee, table, qs[i % R], out=(o[0][e], o[1][e], o[2][e], o[3][e]))
+            for i in range(3):
+                step(i)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(steps):
+                    step(i)
+            g.replay()
+            stream.synchronize()
+            res[f"{name}_ms_per_step"] = _median_region_ms(stream, g.replay, reps, barrier) / steps
+            del g
+    engine.set_option("fk_pdl", 0)
+    res.update({"per_gpu_batch": per_gpu, "algorithmic_bytes_per_config": 4 * n + 4 * (28 + 24 * n), "steps_per_region": steps, "reps": reps})
+    return res
+
+
+def config5(dev, rank, world, dist, barrier, per_gpu=131072, steps=20, reps=5):
+    """-> {ms_per_step, allreduce_scalars}: graph A (zero grad, forward, loss, backward) -> all-reduce of the flat gradient
+    -> graph B (fused Adam), per step."""
+    torch.manual_seed(7)                                   # identical initial parameters on every rank
+    m = drm.DifferentiableKUKAiiwa(device=dev)
+    for i in range(1, 8):
+        b = m._bodies[i]
+        m.make_link_param_learnable(b.name, "mass", UnconstrainedScalar(init_val=b.inertia.mass().detach().clone()))
+        m.make_link_param_learnable(b.name, "com", UnconstrainedTensor(1, 3, init_tensor=b.inertia.com().detach().clone()))
+        m.make_link_param_learnable(b.name, "inertia_mat", UnconstrainedTensor(3, 3, init_tensor=b.inertia.inertia_mat().detach().clone().reshape(3, 3)))
+    flat = m.fuse_learnable_parameters()
+    q, qd, qdd = sample(m, per_gpu, 1000 + rank, dev)
+    target = torch.randn(per_gpu, 7, device=dev)
+    opt = torch.optim.Adam([flat], lr=1e-3, capturable=True, fused=True)
+    flat.grad = torch.zeros_like(flat)
+    stream = torch.cuda.Stream(device=dev)
+
+    def fwd_bwd():
+        flat.grad.zero_()
+        with m.shared_link_table():
+            pos, quat, jl, ja = m.compute_fk_and_jacobian(q, "iiwa_link_ee")
+            tau = m.compute_inverse_dynamics(q, qd, qdd)
+        loss = (tau - target).square().mean() + pos.square().mean()
+        loss.backward()
+        return loss
+
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            fwd_bwd()
+            if world > 1:
+                dist.all_reduce(flat.grad)
+            opt.step()
+        stream.synchronize()
+        mode = "one CUDA graph per step: zero grad, FK+Jacobian, RNEA, loss, backward to one flat gradient, NCCL all-reduce of it, fused Adam"
+        try:                                               # NCCL collectives are graph-capturable: the whole step in ONE graph
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1, stream=stream):
+                loss = fwd_bwd()
+                if world > 1:
+                    dist.all_reduce(flat.grad)
+                opt.step()
+
+            def region():
+                for _ in range(steps):
+                    g1.replay()
+        except Exception as exc:                           # fall back: graph A -> eager all-reduce -> graph B
+            mode = f"CUDA graph (forward, loss, backward) -> eager NCCL all-reduce -> CUDA graph (fused Adam) [single-graph capture failed: {type(exc).__name__}]"
+            torch.cuda.synchronize(dev)
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, stream=stream):
+                loss = fwd_bwd()
+            with torch.cuda.graph(gb, stream=stream):
+                opt.step()
+
+            def region():
+                for _ in range(steps):
+                    ga.replay()
+                    if world > 1:
+                        dist.all_reduce(flat.grad)
+                    gb.replay()
+
+        region()
+        stream.synchronize()
+        ms = _median_region_ms(stream, region, reps, barrier) / steps
+    return {"per_gpu_batch": per_gpu, "ms_per_step": ms, "allreduce_scalars": int(flat.numel()) if world > 1 else 0,
+            "final_loss": float(loss), "algorithmic_bytes_per_config": 420, "steps_per_region": steps, "reps": reps,
+            "step": mode}
+
+
+if __name__ == "__main__":
+    import json
+    d = torch.device("cuda", 0)
+    torch.cuda.set_device(d)
+    print(json.dumps({"config4": config4(d, 0, torch.cuda.synchronize), "config5": config5(d, 0, 1, None, torch.cuda.synchronize)}))
