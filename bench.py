@@ -515,7 +515,8 @@ def main():
                     "collective": "none (batch-sharded)"},
                 "config5_kuka_fk_jac_rnea_backward_adam": {
                     "global_batch": b5 * world, "per_gpu_batch": b5, "ms_per_step": t5, "configs_per_s": world * b5 / (t5 * 1e-3),
-                    "allreduce_scalars_per_step": c5["allreduce_scalars"], "step": c5["step"], "final_loss_rank0": c5["final_loss"]},
+                    "allreduce_scalars_per_step": c5["allreduce_scalars"], "step": c5["step"], "final_loss_rank0": c5["final_loss"],
+                    "ms_per_step_with_nccl_allreduce_and_torch_adam_this_rank": c5["ms_per_step_nccl_allreduce_torch_adam"]},
                 "timing": "median over repetitions per rank, max over ranks; weak scaling (fixed per-GPU shard)"}
         except Exception as exc:                              # report, do not hide
             result["sharded_configs"] = {"error": f"{type(exc).__name__}: {exc}"}

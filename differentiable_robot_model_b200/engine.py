@@ -70,6 +70,13 @@ _SIGNATURES = {
     "drmb200_build_link_table_fused_backward": (ctypes.c_int, [_c_float_p, _c_float_p, _c_float_p, ctypes.c_void_p,
                                                                ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, _c_float_p,
                                                                _c_float_p, ctypes.c_void_p]),
+    "drmb200_comm_create": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p),
+                                           ctypes.c_void_p]),
+    "drmb200_comm_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "drmb200_comm_destroy": (ctypes.c_int, [ctypes.c_void_p]),
+    "drmb200_comm_error": (ctypes.c_int, [ctypes.c_void_p]),
+    "drmb200_allreduce_adam": (ctypes.c_int, [ctypes.c_void_p, _c_float_p, _c_float_p, _c_float_p, _c_float_p, ctypes.c_int32,
+                                              ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_void_p]),
     "drmb200_fk_jacobian_host": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, ctypes.c_int32, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p]),

@@ -84,6 +84,71 @@ def allreduce_link_param_grads(model) -> int:
     return off
 
 
+class PeerAllReduceAdam:
+    """SUM all-reduce of ``param.grad`` over NVLink peer memory FUSED with the Adam update: ONE kernel per step
+    (``drmb200_allreduce_adam``, ``csrc/comm.cu``), no NCCL call, CUDA-graph capturable.  For the flat parameter vector of
+    ``model.fuse_learnable_parameters()`` on a batch that is sharded over the GPUs of one node: every rank calls
+    ``step()`` once per iteration after ``backward()``; all ranks end with bit-identical parameters (rank-ordered sum).
+    ``torch.distributed`` is only used once, at construction, to exchange the 64-byte CUDA IPC handles of the inboxes.
+    With a single process it degenerates to a fused Adam step.  Same arithmetic as ``torch.optim.Adam`` (defaults)."""
+
+    def __init__(self, param: torch.nn.Parameter, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, group=None):
+        import ctypes
+        from . import engine
+        if not param.is_cuda or param.dtype != torch.float32 or not param.is_contiguous():
+            raise RuntimeError("PeerAllReduceAdam needs a contiguous fp32 CUDA parameter")
+        self.param, self.lr, self.betas, self.eps = param, float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        self.exp_avg = torch.zeros_like(param.data)
+        self.exp_avg_sq = torch.zeros_like(param.data)
+        active = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if active else 1
+        self.rank = dist.get_rank(group) if active else 0
+        self._lib = engine.lib()
+        self._comm = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(param.device):
+            engine._check(self._lib.drmb200_comm_create(self.rank, self.world, max(1, param.numel()), ctypes.byref(self._comm),
+                                                        handle), "drmb200_comm_create")
+            if self.world > 1:
+                mine = torch.tensor(list(handle), dtype=torch.uint8, device=param.device)
+                everyone = [torch.empty_like(mine) for _ in range(self.world)]
+                dist.all_gather(everyone, mine, group=group)
+                blob = bytes(torch.cat(everyone).cpu().tolist())
+                engine._check(self._lib.drmb200_comm_connect(self._comm, blob), "drmb200_comm_connect")
+                dist.barrier(group=group)                 # every inbox is mapped before anyone writes into it
+
+    def zero_grad(self, set_to_none: bool = False):
+        if self.param.grad is not None:
+            if set_to_none:
+                self.param.grad = None
+            else:
+                self.param.grad.zero_()
+
+    def step(self):
+        from . import engine
+        g = self.param.grad
+        if g is None:
+            raise RuntimeError("PeerAllReduceAdam.step(): the parameter has no gradient (every rank must step every iteration)")
+        g = g.contiguous()
+        with torch.cuda.device(self.param.device):
+            rc = self._lib.drmb200_allreduce_adam(self._comm, engine._ptr(self.param.data), engine._ptr(g), engine._ptr(self.exp_avg),
+                                                  engine._ptr(self.exp_avg_sq), self.param.numel(), self.lr, self.betas[0],
+                                                  self.betas[1], self.eps, engine._stream())
+        engine._check(rc, "drmb200_allreduce_adam")
+
+    def peer_timeout(self) -> bool:
+        """True if a peer failed to show up within ~2 s in some step (synchronises the device)."""
+        return self._lib.drmb200_comm_error(self._comm) != 0
+
+    def __del__(self):
+        try:
+            if getattr(self, "_comm", None) is not None and self._comm.value:
+                self._lib.drmb200_comm_destroy(self._comm)
+                self._comm = None
+        except Exception:
+            pass
+
+
 def bind_to_device_numa_node(device_index: int) -> bool:
     """Pin the calling process to the CPU cores closest to GPU ``device_index`` (NVML's ideal affinity).
 

@@ -261,6 +261,26 @@ int drmb200_fk_jacobian_host(const drmb200_topology_t* topo, int32_t ee_link, in
                              float* pos_host, float* quat_host,
                              float* jac_lin_host, float* jac_ang_host);
 
+/*
+ * The one exchange step of the data path (parameter learning on a sharded batch, BASELINE config 5): SUM all-reduce of the
+ * flat link-parameter gradient over NVLink peer memory FUSED with the Adam update -- one kernel, no NCCL call, graph
+ * capturable.  One process per GPU; the reference has no distributed code, this is new surface (csrc/comm.cu).
+ *   drmb200_comm_create   allocates this rank's inbox on the current device and returns its 64-byte CUDA IPC handle;
+ *   drmb200_comm_connect  takes the handles of ALL ranks (world * 64 bytes, in rank order; exchanged by the host, e.g.
+ *                         with one torch.distributed all_gather) and maps the peers' inboxes;
+ *   drmb200_allreduce_adam  param [n] (in place), grad [n] (this rank's shard gradient), exp_avg / exp_avg_sq [n] Adam state;
+ *                         every rank must launch it once per step; all ranks end up with bit-identical parameters
+ *                         (rank-ordered sum).  torch.optim.Adam arithmetic (no weight decay / amsgrad).
+ *   drmb200_comm_error    1 if a peer failed to arrive within ~2 s (the kernel never spins forever), -1 on a CUDA error.
+ */
+typedef struct drmb200_comm drmb200_comm_t;
+int drmb200_comm_create(int32_t rank, int32_t world, int32_t max_floats, drmb200_comm_t** comm, void* ipc_handle_out);
+int drmb200_comm_connect(drmb200_comm_t* comm, const void* all_ipc_handles);
+int drmb200_comm_destroy(drmb200_comm_t* comm);
+int drmb200_comm_error(drmb200_comm_t* comm);
+int drmb200_allreduce_adam(drmb200_comm_t* comm, float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                           int32_t n, float lr, float beta1, float beta2, float eps, void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,7 +98,9 @@ def config5(dev, rank, world, dist, barrier, per_gpu=131072, steps=20, reps=5):
     flat = m.fuse_learnable_parameters()
     q, qd, qdd = sample(m, per_gpu, 1000 + rank, dev)
     target = torch.randn(per_gpu, 7, device=dev)
-    opt = torch.optim.Adam([flat], lr=1e-3, capturable=True, fused=True)
+    from differentiable_robot_model_b200.parallel import PeerAllReduceAdam
+    peer_opt = PeerAllReduceAdam(flat, lr=1e-3)           # NVLink peer-memory all-reduce fused with Adam: one kernel
+    opt = torch.optim.Adam([flat], lr=1e-3, capturable=True, fused=True)      # the NCCL + torch baseline beside it
     flat.grad = torch.zeros_like(flat)
     stream = torch.cuda.Stream(device=dev)
 
@@ -118,38 +120,41 @@ def config5(dev, rank, world, dist, barrier, per_gpu=131072, steps=20, reps=5):
                 dist.all_reduce(flat.grad)
             opt.step()
         stream.synchronize()
-        mode = "one CUDA graph per step: zero grad, FK+Jacobian, RNEA, loss, backward to one flat gradient, NCCL all-reduce of it, fused Adam"
-        try:                                               # NCCL collectives are graph-capturable: the whole step in ONE graph
-            g1 = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1, stream=stream):
-                loss = fwd_bwd()
-                if world > 1:
+        mode = ("one CUDA graph per step: zero grad, FK+Jacobian, RNEA, loss, backward to one flat gradient, then ONE kernel: "
+                "peer-memory SUM all-reduce of the gradient over NVLink fused with the Adam update (csrc/comm.cu)")
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, stream=stream):
+            loss = fwd_bwd()
+            peer_opt.step()
+
+        def region():
+            for _ in range(steps):
+                g1.replay()
+
+        nccl_ms = None
+        if world > 1:                                      # the baseline: same step with an NCCL all-reduce + torch's fused Adam
+            try:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, stream=stream):
+                    fwd_bwd()
                     dist.all_reduce(flat.grad)
-                opt.step()
+                    opt.step()
 
-            def region():
-                for _ in range(steps):
-                    g1.replay()
-        except Exception as exc:                           # fall back: graph A -> eager all-reduce -> graph B
-            mode = f"CUDA graph (forward, loss, backward) -> eager NCCL all-reduce -> CUDA graph (fused Adam) [single-graph capture failed: {type(exc).__name__}]"
-            torch.cuda.synchronize(dev)
-            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ga, stream=stream):
-                loss = fwd_bwd()
-            with torch.cuda.graph(gb, stream=stream):
-                opt.step()
-
-            def region():
-                for _ in range(steps):
-                    ga.replay()
-                    if world > 1:
-                        dist.all_reduce(flat.grad)
-                    gb.replay()
+                def region_nccl():
+                    for _ in range(steps):
+                        g2.replay()
+                region_nccl()
+                stream.synchronize()
+                nccl_ms = _median_region_ms(stream, region_nccl, reps, barrier) / steps
+            except Exception as exc:
+                nccl_ms = f"capture failed: {type(exc).__name__}"
 
         region()
         stream.synchronize()
         ms = _median_region_ms(stream, region, reps, barrier) / steps
-    return {"per_gpu_batch": per_gpu, "ms_per_step": ms, "allreduce_scalars": int(flat.numel()) if world > 1 else 0,
+    assert not peer_opt.peer_timeout(), "a peer did not arrive in the fused all-reduce"
+    return {"per_gpu_batch": per_gpu, "ms_per_step": ms, "ms_per_step_nccl_allreduce_torch_adam": nccl_ms,
+            "allreduce_scalars": int(flat.numel()) if world > 1 else 0,
             "final_loss": float(loss), "algorithmic_bytes_per_config": 420, "steps_per_region": steps, "reps": reps,
             "step": mode}
 
