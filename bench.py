@@ -416,7 +416,8 @@ def main():
         warm_replays = max(1, (args.warmup - 64) // max(1, min(GRAPH_NODES, args.steps)))
         if sampler:
             sampler.mark_start()
-        region_ms, launch_desc = timed_regions(args.steps, args.reps, pdl=2, branches=1, warm_replays=warm_replays)
+        head_branches = max(1, min(4, int(os.environ.get("DRMB200_BENCH_BRANCHES", "1"))))
+        region_ms, launch_desc = timed_regions(args.steps, args.reps, pdl=2, branches=head_branches, warm_replays=warm_replays)
         if sampler:
             sampler.mark_end()
         elapsed_ms = job_ms(region_ms)

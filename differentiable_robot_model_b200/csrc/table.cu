@@ -142,10 +142,27 @@ __global__ void scatter_flat_grad_kernel(const float* __restrict__ g_raw, const 
     }
 }
 
+// The link-table build is usually the library's first launch in a process whose CUDA context was created by another runtime
+// instance (torch's).  When that first call is a plain <<<>>> launch, this library's (statically linked) runtime probes
+// cuKernelGetFunction before it has loaded its module into the context; the probe returns CUDA_ERROR_INVALID_HANDLE
+// internally, the runtime then loads the module and the launch succeeds -- harmless, but compute-sanitizer reports the
+// internal return code as "1 error" (the r01 memcheck logs; reproduced and bisected with scripts/gpu_sanitize_r02.sh: the
+// error appears iff this kernel is the first call and vanishes when an attribute query comes first).  So: query first.
+static void warm_runtime_once() {
+    static bool done_by_dev[64] = {false};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return; }
+    if (done_by_dev[dev & 63]) return;
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, build_table_kernel) != cudaSuccess) cudaGetLastError();
+    done_by_dev[dev & 63] = true;
+}
+
 int build_table_fused_device(const float* const_raw, const float* flat, const int32_t* src, const int32_t* kind,
                              const float* off, int32_t n_links, float* raw_out, float* table, cudaStream_t stream) {
     if (n_links < 1 || n_links > DRMB200_MAX_LINKS) { set_error("n_links=%d outside [1, %d]", n_links, DRMB200_MAX_LINKS); return DRMB200_ELIMIT; }
     if (const_raw == nullptr || flat == nullptr || src == nullptr || kind == nullptr || off == nullptr || raw_out == nullptr || table == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    warm_runtime_once();
     build_table_fused_kernel<<<1, 64, 0, stream>>>(const_raw, flat, src, kind, off, n_links, raw_out, table);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("build_table_fused launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
@@ -169,6 +186,7 @@ int build_table_fused_backward_device(const float* raw, const float* g_table, co
 int build_table_device(const float* raw, int32_t n_links, float* table, cudaStream_t stream) {
     if (n_links < 1 || n_links > DRMB200_MAX_LINKS) { set_error("n_links=%d outside [1, %d]", n_links, DRMB200_MAX_LINKS); return DRMB200_ELIMIT; }
     if (raw == nullptr || table == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    warm_runtime_once();
     build_table_kernel<<<1, 64, 0, stream>>>(raw, n_links, table);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("build_table launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
