@@ -424,7 +424,7 @@ def main():
 
         modes = None
         if not args.no_modes:
-            k = min(args.steps, 2048)
+            k = 2048                                        # enough launches that the ramp of the first one is amortised
             r = min(args.reps, 7)
             modes = {"steps_per_region": k, "reps": r,
                      "stream_ordered_pdl_us": job_ms(timed_regions(k, r, 2, 1, 1)[0]) * 1e3 / k,
