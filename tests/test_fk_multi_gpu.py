@@ -111,3 +111,28 @@ def test_multi_argument_errors():
         m.compute_fk_and_jacobian_multi(q, ["iiwa_link_ee", "iiwa_link_ee"])
     with pytest.raises(RuntimeError):
         m.compute_fk_and_jacobian_multi(q, [f"iiwa_link_{i}" for i in range(8)] + ["iiwa_link_ee"])     # 9 > 8 links
+
+
+@pytest.mark.parametrize("stem", ["allegro_hand_description_left", "iiwa7_allegro", "trifinger_edu"])
+def test_multi_output_subsets_and_unaligned_inputs(stem):
+    """Pose-only / Jacobian-only launches (other template instantiations of the tree kernel) and a q whose base pointer is
+    not 16-byte aligned (cooperative-copy staging instead of TMA bulk copies) give the same bits."""
+    m = model(stem)
+    robot = O.load_robot(urdf_path(stem), torch.float32)
+    links = [m._name_to_idx_map[n] for n in CASES[stem]]
+    table, topo = m._link_table(), m._topology
+    for batch in (257, 2048):
+        q = O.sample_inputs(robot, batch + 1, seed=3)[0].to(DEV)
+        full = engine.fk_jacobian_multi_raw(topo, links, table, q[1:].contiguous())
+        pos, quat, none1, none2 = engine.fk_jacobian_multi_raw(topo, links, table, q[1:].contiguous(), want_jac=False)
+        assert none1 is None and none2 is None and torch.equal(pos, full[0]) and torch.equal(quat, full[1])
+        p2, q2, jl, ja = engine.fk_jacobian_multi_raw(topo, links, table, q[1:].contiguous(), want_pos=False, want_quat=False)
+        assert p2 is None and q2 is None and torch.equal(jl, full[2]) and torch.equal(ja, full[3])
+        # unaligned: the same rows one float into a fresh allocation
+        flat = torch.empty(batch * q.shape[1] + 1, device=DEV)
+        flat[1:] = q[1:].reshape(-1)
+        q_un = flat[1:].view(batch, q.shape[1])
+        assert q_un.data_ptr() % 16 != 0 and q_un.is_contiguous()
+        un = engine.fk_jacobian_multi_raw(topo, links, table, q_un)
+        for a, b in zip(un, full):
+            assert torch.equal(a, b)
