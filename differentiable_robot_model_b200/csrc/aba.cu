@@ -183,7 +183,7 @@ __device__ __forceinline__ void sub_outer_pp(M3PP& m, V3 x, const V3P& yp) {
 
 template <int T>
 __global__ void __launch_bounds__(T)
-aba_kernel(const __grid_constant__ TreeProgram prog, const AbaArgs args) {
+aba_kernel(const __grid_constant__ TreeProgram prog, const __grid_constant__ FoldProgram fold, const AbaArgs args) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t mbar;
 
@@ -219,7 +219,10 @@ aba_kernel(const __grid_constant__ TreeProgram prog, const AbaArgs args) {
         coop_copy(s_qd, args.qd + tile_start * n, valid * n, vec_ok);
         coop_copy(s_f, args.f + tile_start * n, valid * n, vec_ok);
     }
-    stage_canonical_table(s_tab, args.table, prog, T);
+    // fold.n_red > 0: fixed links folded into their movable ancestors, prog is the reduced tree (drm_common.cuh): a fixed
+    // joint has S = 0, so its articulated inertia and bias force pass to the parent through a constant transform -- the fold
+    if (fold.n_red > 0) stage_folded_table(s_tab, s_link, args.table, fold, prog, T);
+    else stage_canonical_table(s_tab, args.table, prog, T);
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
 
@@ -408,7 +411,7 @@ aba_kernel(const __grid_constant__ TreeProgram prog, const AbaArgs args) {
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int T>
-static int launch_aba(const TreeProgram& prog, const AbaArgs& args, size_t smem_bytes, cudaStream_t stream) {
+static int launch_aba(const TreeProgram& prog, const FoldProgram& fold, const AbaArgs& args, size_t smem_bytes, cudaStream_t stream) {
     static size_t configured_by_dev[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -420,7 +423,7 @@ static int launch_aba(const TreeProgram& prog, const AbaArgs& args, size_t smem_
     }
     const int64_t tiles = (args.batch + T - 1) / T;
     if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
-    aba_kernel<T><<<(unsigned)tiles, T, smem_bytes, stream>>>(prog, args);
+    aba_kernel<T><<<(unsigned)tiles, T, smem_bytes, stream>>>(prog, fold, args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("aba launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
@@ -429,9 +432,13 @@ static int launch_aba(const TreeProgram& prog, const AbaArgs& args, size_t smem_
 
 int forward_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
                             const float* f, int64_t batch, uint32_t flags, float* qdd, cudaStream_t stream) {
-    TreeProgram prog;
-    int rc = build_tree_program(topo, &prog);
-    if (rc != DRMB200_OK) return rc;
+    int rc;
+    const CachedPrograms* cp = cached_programs(topo, &rc);
+    if (cp == nullptr) return rc;
+    const bool folded = cp->foldable && get_option(11) != 0;      // "rnea_fold"
+    const TreeProgram& prog = folded ? cp->red : cp->full;
+    FoldProgram fold = cp->fold;
+    if (!folded) fold.n_red = 0;
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
     if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr || qd == nullptr || f == nullptr || qdd == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
@@ -446,7 +453,7 @@ int forward_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     const int tile = bytes_of(64) <= 113 * 1024 ? 64 : 32;
     const size_t smem_bytes = bytes_of(tile);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
-    return tile == 64 ? launch_aba<64>(prog, args, smem_bytes, stream) : launch_aba<32>(prog, args, smem_bytes, stream);
+    return tile == 64 ? launch_aba<64>(prog, fold, args, smem_bytes, stream) : launch_aba<32>(prog, fold, args, smem_bytes, stream);
 }
 
 }  // namespace drm

@@ -42,7 +42,7 @@ struct MmSmemLayout {
 
 template <int T>
 __global__ void __launch_bounds__(T)
-mass_matrix_kernel(const __grid_constant__ TreeProgram prog, const MmArgs args) {
+mass_matrix_kernel(const __grid_constant__ TreeProgram prog, const __grid_constant__ FoldProgram fold, const MmArgs args) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t mbar;
 
@@ -72,7 +72,9 @@ mass_matrix_kernel(const __grid_constant__ TreeProgram prog, const MmArgs args) 
     } else {
         coop_copy(s_q, args.q + tile_start * n, valid * n, vec_ok);
     }
-    stage_canonical_table(s_tab, args.table, prog, T);
+    // fold.n_red > 0: fixed links folded into their movable ancestors, prog is the reduced tree (drm_common.cuh)
+    if (fold.n_red > 0) stage_folded_table(s_tab, s_link, args.table, fold, prog, T);
+    else stage_canonical_table(s_tab, args.table, prog, T);
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
 
@@ -157,7 +159,7 @@ mass_matrix_kernel(const __grid_constant__ TreeProgram prog, const MmArgs args) 
 }
 
 template <int T>
-static int launch_mm(const TreeProgram& prog, const MmArgs& args, size_t smem_bytes, cudaStream_t stream) {
+static int launch_mm(const TreeProgram& prog, const FoldProgram& fold, const MmArgs& args, size_t smem_bytes, cudaStream_t stream) {
     static size_t configured_by_dev[64] = {0};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -169,7 +171,7 @@ static int launch_mm(const TreeProgram& prog, const MmArgs& args, size_t smem_by
     }
     const int64_t tiles = (args.batch + T - 1) / T;
     if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
-    mass_matrix_kernel<T><<<(unsigned)tiles, T, smem_bytes, stream>>>(prog, args);
+    mass_matrix_kernel<T><<<(unsigned)tiles, T, smem_bytes, stream>>>(prog, fold, args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("mass matrix launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
@@ -178,9 +180,14 @@ static int launch_mm(const TreeProgram& prog, const MmArgs& args, size_t smem_by
 
 int mass_matrix_device(const drmb200_topology_t* topo, const float* table, const float* q, int64_t batch, float* H,
                        cudaStream_t stream) {
-    TreeProgram prog;
-    int rc = build_tree_program(topo, &prog);
-    if (rc != DRMB200_OK) return rc;
+    int rc;
+    const CachedPrograms* cp = cached_programs(topo, &rc);
+    if (cp == nullptr) return rc;
+    // "rnea_fold": walk only the movable links (fixed links folded into their movable ancestors while the table is staged)
+    const bool folded = cp->foldable && get_option(11) != 0;
+    const TreeProgram& prog = folded ? cp->red : cp->full;
+    FoldProgram fold = cp->fold;
+    if (!folded) fold.n_red = 0;                        // the kernel's "no folding" flag
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
     if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr || H == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
@@ -192,7 +199,7 @@ int mass_matrix_device(const drmb200_topology_t* topo, const float* table, const
     const int tile = bytes_of(64) <= 113 * 1024 ? 64 : 32;
     const size_t smem_bytes = bytes_of(tile);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
-    return tile == 64 ? launch_mm<64>(prog, args, smem_bytes, stream) : launch_mm<32>(prog, args, smem_bytes, stream);
+    return tile == 64 ? launch_mm<64>(prog, fold, args, smem_bytes, stream) : launch_mm<32>(prog, fold, args, smem_bytes, stream);
 }
 
 }  // namespace drm

@@ -79,9 +79,9 @@ struct RneaSmemLayout {
 // (A per-warp pipeline version of this kernel -- persistent grid, no CTA barrier, like fk_tree.cu -- was measured at
 // 10.2 G cfg/s against 11.3 G for this CTA-tile form on the Panda: the kernel is issue-bound and the extra loop /
 // addressing instructions cost more than the barrier stalls they remove.)
-template <int T, bool PACKED, bool DUMP>
+template <int T, bool PACKED, bool DUMP, bool FOLD>
 __global__ void __launch_bounds__(T)
-rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
+rnea_kernel(const __grid_constant__ TreeProgram prog, const __grid_constant__ FoldProgram fold, const RneaArgs args) {
     extern __shared__ __align__(128) float smem[];
     __shared__ __align__(8) uint64_t mbar;
 
@@ -117,7 +117,8 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const RneaArgs args) {
         coop_copy(s_qd, args.qd + tile_start * n, valid * n, vec_ok);
         coop_copy(s_qdd, args.qdd + tile_start * n, valid * n, vec_ok);
     }
-    stage_canonical_table(s_tab, args.table, prog, T);
+    if (FOLD) stage_folded_table(s_tab, s_link, args.table, fold, prog, T);      // s_link: scratch until the walk starts
+    else stage_canonical_table(s_tab, args.table, prog, T);
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
 
@@ -370,14 +371,14 @@ int build_tree_program(const drmb200_topology_t* topo, TreeProgram* prog) {
     return DRMB200_OK;
 }
 
-template <int T, bool PACKED, bool DUMP>
-static int launch_rnea(const TreeProgram& prog, const RneaArgs& args, cudaStream_t stream) {
+template <int T, bool PACKED, bool DUMP, bool FOLD>
+static int launch_rnea(const TreeProgram& prog, const FoldProgram& fold, const RneaArgs& args, cudaStream_t stream) {
     const RneaSmemLayout L(T, prog.n_dofs, prog.n_links, prog.n_slots);
     const size_t smem_bytes = (size_t)L.total_floats * sizeof(float);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
     const int64_t tiles = (args.batch + T - 1) / T;
     if (tiles > 0x7fffffffLL) { set_error("batch too large for one launch"); return DRMB200_EINVAL; }
-    auto kern = rnea_kernel<T, PACKED, DUMP>;
+    auto kern = rnea_kernel<T, PACKED, DUMP, FOLD>;
     static size_t configured_by_dev[64] = {0};     // per instantiation, per device
     int dev = 0;
     cudaGetDevice(&dev);
@@ -387,38 +388,84 @@ static int launch_rnea(const TreeProgram& prog, const RneaArgs& args, cudaStream
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(%zu B smem): %s", smem_bytes, cudaGetErrorString(e)); return DRMB200_ECUDA; }
         configured = smem_bytes;
     }
-    kern<<<(unsigned)tiles, T, smem_bytes, stream>>>(prog, args);
+    kern<<<(unsigned)tiles, T, smem_bytes, stream>>>(prog, fold, args);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("rnea launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
     return DRMB200_OK;
 }
 
-// the tree program depends only on the topology: keep the last two per thread
-static const TreeProgram* cached_tree_program(const drmb200_topology_t* topo, int* rc_out) {
-    struct Cached { bool valid; drmb200_topology_t topo; TreeProgram prog; };
-    static thread_local Cached cache[2] = {};
+// the tree program (and the folded one) depend only on the topology: keep the last two per thread
+
+static int build_fold(const drmb200_topology_t* topo, TreeProgram* red, FoldProgram* fold, bool* foldable) {
+    const int N = topo->n_links;
+    memset(fold, 0, sizeof(*fold));
+    fold->n_full = N;
+    drmb200_topology_t rt;
+    memset(&rt, 0, sizeof(rt));
+    int n_red = 1, n_fixed = 0;
+    fold->full_of[0] = 0; fold->red_of[0] = 0; fold->parent[0] = -1; fold->axis[0] = 0;
+    rt.parent[0] = -1; rt.axis[0] = 0; rt.dof[0] = -1;
+    for (int l = 1; l < N; ++l) {
+        fold->parent[l] = topo->parent[l];
+        fold->axis[l] = topo->axis[l];
+        if (topo->axis[l] != 0) {
+            const int j = n_red++;
+            fold->full_of[j] = (int8_t)l;
+            fold->red_of[l] = (int8_t)j;
+            rt.parent[j] = fold->red_of[topo->parent[l]];          // anchor of the parent: nearest movable ancestor, or the root
+            rt.axis[j] = topo->axis[l];
+            rt.dof[j] = topo->dof[l];
+        } else {
+            fold->red_of[l] = fold->red_of[topo->parent[l]];
+            ++n_fixed;
+        }
+    }
+    fold->n_red = n_red;
+    int e = 0;
+    for (int j = 0; j < n_red; ++j) {
+        fold->carry_start[j] = (int8_t)e;
+        if (j == 0) continue;                              // links fixed to the root load no joint
+        for (int l = 1; l < N; ++l)
+            if (topo->axis[l] == 0 && fold->red_of[l] == j) fold->carry[e++] = (int8_t)l;
+    }
+    fold->carry_start[n_red] = (int8_t)e;
+    rt.n_links = n_red;
+    rt.n_dofs = topo->n_dofs;
+    // staging scratch (raw table + poses, 40 floats per original link) lives in the per-link state region (8 floats per
+    // reduced link and configuration) of the smallest tile any of the tree kernels uses (32 configurations)
+    *foldable = n_fixed > 0 && n_red > 1 && N * 40 <= n_red * 8 * 32;
+    return build_tree_program(&rt, red);
+}
+
+const CachedPrograms* cached_programs(const drmb200_topology_t* topo, int* rc_out) {
+    static thread_local CachedPrograms cache[2] = {};
     static thread_local int next = 0;
     *rc_out = DRMB200_OK;
     if (topo == nullptr) { set_error("topology is null"); *rc_out = DRMB200_EINVAL; return nullptr; }
-    for (auto& c : cache) if (c.valid && memcmp(&c.topo, topo, sizeof(*topo)) == 0) return &c.prog;
-    Cached& c = cache[next];
+    for (auto& c : cache) if (c.valid && memcmp(&c.topo, topo, sizeof(*topo)) == 0) return &c;
+    CachedPrograms& c = cache[next];
     c.valid = false;
-    *rc_out = build_tree_program(topo, &c.prog);
+    *rc_out = build_tree_program(topo, &c.full);
+    if (*rc_out != DRMB200_OK) return nullptr;
+    *rc_out = build_fold(topo, &c.red, &c.fold, &c.foldable);
     if (*rc_out != DRMB200_OK) return nullptr;
     c.topo = *topo; c.valid = true;
     next ^= 1;
-    return &c.prog;
+    return &c;
 }
 
 int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
                             const float* qdd, int64_t batch, uint32_t flags, float* tau, cudaStream_t stream) {
     int rc;
-    const TreeProgram* prog = cached_tree_program(topo, &rc);
-    if (prog == nullptr) return rc;
+    const CachedPrograms* cp = cached_programs(topo, &rc);
+    if (cp == nullptr) return rc;
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
-    if (batch == 0 || prog->n_dofs == 0) return DRMB200_OK;
+    if (batch == 0 || cp->full.n_dofs == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr || qd == nullptr || qdd == nullptr || tau == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    // "rnea_fold" (default on): walk only the movable links, fixed links folded into their movable ancestors at staging time
+    const bool fold = cp->foldable && get_option(11) != 0;
+    const TreeProgram* prog = fold ? &cp->red : &cp->full;
     // tile: 64 for batches that would not fill two waves of 128-row CTAs (more, smaller CTAs balance the SMs and the
     // shared-memory-limited residency is the same number of warps), and for models whose 128-row footprint is too big
     int tile = (batch <= 148 * 1024) ? 64 : 128;
@@ -429,8 +476,12 @@ int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
     const bool packed = get_option(4) != 0;             // "rnea_packed": FP32x2 arithmetic (default) vs scalar, for A/B runs
-    if (tile == 64) return packed ? launch_rnea<64, true, false>(*prog, args, stream) : launch_rnea<64, false, false>(*prog, args, stream);
-    return packed ? launch_rnea<128, true, false>(*prog, args, stream) : launch_rnea<128, false, false>(*prog, args, stream);
+    if (fold) {
+        if (tile == 64) return packed ? launch_rnea<64, true, false, true>(*prog, cp->fold, args, stream) : launch_rnea<64, false, false, true>(*prog, cp->fold, args, stream);
+        return packed ? launch_rnea<128, true, false, true>(*prog, cp->fold, args, stream) : launch_rnea<128, false, false, true>(*prog, cp->fold, args, stream);
+    }
+    if (tile == 64) return packed ? launch_rnea<64, true, false, false>(*prog, cp->fold, args, stream) : launch_rnea<64, false, false, false>(*prog, cp->fold, args, stream);
+    return packed ? launch_rnea<128, true, false, false>(*prog, cp->fold, args, stream) : launch_rnea<128, false, false, false>(*prog, cp->fold, args, stream);
 }
 
 // inverse dynamics + the per-link state of the reference's bodies (vel, acc, force), see rnea_kernel<.., DUMP>
@@ -438,8 +489,9 @@ int dynamic_state_device(const drmb200_topology_t* topo, const float* table, con
                          const float* qdd, int64_t batch, uint32_t flags, float* tau, float* vels, float* accs,
                          float* forces, cudaStream_t stream) {
     int rc;
-    const TreeProgram* prog = cached_tree_program(topo, &rc);
-    if (prog == nullptr) return rc;
+    const CachedPrograms* cp = cached_programs(topo, &rc);
+    if (cp == nullptr) return rc;
+    const TreeProgram* prog = &cp->full;                  // every link reports its state: no folding here
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
     if (batch == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr || qd == nullptr || qdd == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
@@ -448,7 +500,7 @@ int dynamic_state_device(const drmb200_topology_t* topo, const float* table, con
     args.vels = vels; args.accs = accs; args.forces = forces;
     auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
-    return launch_rnea<64, true, true>(*prog, args, stream);
+    return launch_rnea<64, true, true, false>(*prog, cp->fold, args, stream);
 }
 
 }  // namespace drm

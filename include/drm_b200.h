@@ -93,6 +93,8 @@ int64_t drmb200_launch_count(void);        /* kernels launched by this library s
  *   "fk_packed":  1 = packed FP32x2 arithmetic (FFMA2) in the rolled chain walk (default), 0 = scalar FFMA,
  *                 2 = two configurations per thread in the two FP32x2 lanes (measured slower; kept for A/B);
  *   "rnea_packed": 1 = packed FP32x2 arithmetic in the inverse-dynamics kernel (default), 0 = scalar FFMA;
+ *   "rnea_fold":  1 = the inverse-dynamics kernel walks only the movable links, links behind fixed joints are folded into
+ *                 their nearest movable ancestor while the table is staged (default), 0 = one step per link like the reference;
  *   "host_fused": drmb200_fk_jacobian_host on page-locked buffers: 1 = one launch whose TMA copies cross PCIe (default),
  *                 0 = staged H2D -> kernel -> D2H pipeline;
  *   "fk_pdl":     programmatic dependent launch of drmb200_fk_jacobian.  0 (default): ordinary stream-ordered launches.

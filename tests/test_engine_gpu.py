@@ -74,12 +74,15 @@ def test_fk_jacobian_matches_reference_golden(robot_stem, fk_variant):
     assert engine.launch_count() - launches == 3 * len(g["fk_links"])
 
 
-@pytest.fixture(params=[1, 0], ids=["packed_f32x2", "scalar"])
+@pytest.fixture(params=[(1, 1), (0, 1), (1, 0), (0, 0)], ids=["packed_folded", "scalar_folded", "packed_every_link", "scalar_every_link"])
 def rnea_variant(request):
-    """Both arithmetic variants of the inverse-dynamics kernel must give the same parity."""
-    engine.set_option("rnea_packed", request.param)
+    """Both arithmetic variants of the inverse-dynamics kernel, with fixed links folded into their movable ancestors
+    (default) and with one step per link like the reference, must give the same parity."""
+    engine.set_option("rnea_packed", request.param[0])
+    engine.set_option("rnea_fold", request.param[1])
     yield request.param
     engine.set_option("rnea_packed", 1)
+    engine.set_option("rnea_fold", 1)
 
 
 def test_inverse_dynamics_matches_reference_golden(robot_stem, rnea_variant):
@@ -424,3 +427,44 @@ def test_large_reference_batches_with_raw_quaternion_sign(stem, fk_variant):
         assert min(int((clear & (branch == b)).sum()) for b in range(4)) >= 40      # each branch asserted with raw sign
     tau = m.compute_inverse_dynamics(q, qd, qdd)
     assert_close(tau.cpu().numpy(), g["tau"], atol=1e-5, what=f"{stem} tau")
+
+
+def test_folded_inverse_dynamics_follows_learnable_parameters_of_fixed_links():
+    """Folding recomputes the composite bodies from the CURRENT table on every launch: learnable inertial parameters of a
+    link behind a fixed joint (iiwa_link_ee) and learnable origins of movable links change tau exactly as without folding."""
+    from differentiable_robot_model_b200.rigid_body_params import UnconstrainedScalar, UnconstrainedTensor
+    robot = O.load_robot(urdf_path("iiwa7"), torch.float32)
+    q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, 777, seed=5))
+    m = gpu_model("iiwa7")
+    m.make_link_param_learnable("iiwa_link_ee", "mass", UnconstrainedScalar(init_val=torch.tensor([2.5])))
+    m.make_link_param_learnable("iiwa_link_ee", "com", UnconstrainedTensor(1, 3, init_tensor=torch.tensor([[0.05, -0.02, 0.1]])))
+    m.make_link_param_learnable("iiwa_link_ee", "inertia_mat", UnconstrainedTensor(3, 3, init_tensor=torch.tensor([[0.02, 0.003, -0.001], [0.001, 0.03, 0.002], [0.004, -0.002, 0.01]])))
+    m.make_link_param_learnable("iiwa_link_6", "trans", UnconstrainedTensor(1, 3, init_tensor=torch.tensor([[0.01, 0.05, 0.2]])))
+    with torch.no_grad():
+        engine.set_option("rnea_fold", 0)
+        want = m.compute_inverse_dynamics(q, qd, qdd)
+        engine.set_option("rnea_fold", 1)
+        got = m.compute_inverse_dynamics(q, qd, qdd)
+    scale = float(want.abs().max())
+    assert_close(got.cpu().numpy() / scale, want.cpu().numpy() / scale, rtol=1e-5, atol=2e-6, what="tau folded vs every link")
+    base = gpu_model("iiwa7").compute_inverse_dynamics(q, qd, qdd)
+    assert float((got - base).abs().max()) > 1e-2 * scale          # the fixed link's parameters do matter
+
+
+@pytest.mark.parametrize("stem", ["iiwa7", "panda", "allegro_hand_description_left", "iiwa7_allegro", "trifinger_edu", "jaco"])
+def test_folding_fixed_links_does_not_change_mass_matrix_or_forward_dynamics(stem):
+    """The mass-matrix and articulated-body kernels walk only the movable links too ("rnea_fold"); one step per link
+    (the reference's loop) must give the same numbers up to rounding."""
+    robot = O.load_robot(urdf_path(stem), torch.float32)
+    q, qd, _ = (t.to(DEV) for t in O.sample_inputs(robot, 300, seed=8))
+    f = torch.randn(300, q.shape[1], generator=torch.Generator().manual_seed(1)).to(DEV)
+    m = gpu_model(stem)
+    out = {}
+    for fold in (0, 1):
+        engine.set_option("rnea_fold", fold)
+        with torch.no_grad():
+            out[fold] = (m.compute_lagrangian_inertia_matrix(q), m.compute_forward_dynamics(q, qd, f, use_damping=True))
+    engine.set_option("rnea_fold", 1)
+    for a, b, what in zip(out[1], out[0], ("H", "qdd")):
+        scale = float(b.abs().max())
+        assert_close(a.cpu().numpy() / scale, b.cpu().numpy() / scale, rtol=2e-5, atol=5e-6, what=f"{stem} {what} folded vs every link")
