@@ -8,12 +8,13 @@ of `iiwa_link_ee`) over one batch of 65 536 synthetic joint configurations (BASE
 configs[1]).  Inputs are resident in HBM before the timed region; the step cycles through ROTATE
 distinct buffer sets (> the 126 MB L2) so no launch finds its data in L2.
 
-Launch pattern of the headline number: the K launches go down ONE stream, strictly stream-ordered,
-replayed from a CUDA graph (the per-launch Python/ctypes overhead would otherwise exceed the ~3 us
-kernel), with programmatic dependent launch enabled in the library (`fk_pdl` = 2, include/drm_b200.h):
-a launch may start its loads and arithmetic while its predecessor is still storing and waits for it
-before its own first global write.  The same kernels without that overlap and in four parallel graph
-branches are reported beside it (`launch_modes`).
+Launch pattern of the headline number: the K launches are replayed from a CUDA graph (the per-launch
+Python/ctypes overhead would otherwise exceed the ~3 us kernel) as four independent chains (graph
+branches; the batches are independent), each chain stream-ordered with programmatic dependent launch
+enabled in the library (`fk_pdl` = 2, include/drm_b200.h): a launch may start its loads and arithmetic
+while its predecessor is still storing and waits for it before its own first global write.
+`launch_modes` reports, per launch: ONE stream with PDL, one stream without any overlap (what a single
+isolated call costs on the device), four branches without PDL (round 1), four branches with PDL.
 
 Timing: the timed region of K steps is repeated REPS times; every repetition is bracketed by a barrier
 + synchronize on both sides and timed with CUDA events on the launching stream, with a GPU-side delay
@@ -24,7 +25,7 @@ repetitions, the job reports the MAX over ranks.
 Extra keys on the JSON line (see DESIGN.md "Measurement"):
   roofline            dominant kernel vs the measured HBM copy bandwidth (MEASURED_PEAKS.json)
   roofline_large_batch  the same kernel on 2^22 configurations per launch (the asymptotic figure)
-  launch_modes        us per launch: stream-ordered + PDL (the headline), stream-ordered, 4 graph branches
+  launch_modes        us per launch: one stream + PDL, one stream, 4 graph branches, 4 branches + PDL (the headline)
   e2e                 same metric through the host-buffer C-ABI call (H2D + kernel + D2H per step)
   cpu_baseline        the UNMODIFIED reference (baseline/_ref) on the host cores, bounded sample
   cpu_baseline_port   the vectorised torch CPU port of the same algorithm (oracle/drm_oracle.py)
@@ -416,7 +417,10 @@ def main():
         warm_replays = max(1, (args.warmup - 64) // max(1, min(GRAPH_NODES, args.steps)))
         if sampler:
             sampler.mark_start()
-        head_branches = max(1, min(4, int(os.environ.get("DRMB200_BENCH_BRANCHES", "1"))))
+        # headline pattern: 4 independent chains of launches (graph branches), each chain stream-ordered with programmatic
+        # dependent launch -- the batches are independent, and a 20-step region amortises the first launch's latency best
+        # that way (63 us against 65.5 us for one chain); one chain alone is reported in `launch_modes`
+        head_branches = max(1, min(4, int(os.environ.get("DRMB200_BENCH_BRANCHES", "4"))))
         region_ms, launch_desc = timed_regions(args.steps, args.reps, pdl=2, branches=head_branches, warm_replays=warm_replays)
         if sampler:
             sampler.mark_end()
@@ -430,8 +434,10 @@ def main():
                      "stream_ordered_pdl_us": job_ms(timed_regions(k, r, 2, 1, 1)[0]) * 1e3 / k,
                      "stream_ordered_us": job_ms(timed_regions(k, r, 0, 1, 1)[0]) * 1e3 / k,
                      "branches4_us": job_ms(timed_regions(k, r, 0, 4, 1)[0]) * 1e3 / k,
-                     "note": "us per 65536-configuration launch (median of reps, max over ranks); stream_ordered = one launch "
-                             "after the other with nothing overlapping, i.e. what a single isolated call costs on the device"}
+                     "branches4_pdl_us": job_ms(timed_regions(k, r, 2, 4, 1)[0]) * 1e3 / k,
+                     "note": "us per 65536-configuration launch (median of reps, max over ranks): ONE stream with programmatic "
+                             "dependent launch (fk_pdl 2) / one stream, nothing overlapping = what a single isolated call costs "
+                             "on the device / four graph branches (round 1's pattern) / four branches with PDL (the headline)"}
         engine.set_option("fk_pdl", 2)
 
     gpu_launches = args.steps                                    # fk_jacobian_kernel launches inside ONE timed region

@@ -124,6 +124,25 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _NoGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_GUARD = _NoGuard()
+
+
+def _on(device):
+    """Context that makes `device` current for a launch.  A no-op object when it already is (the usual case): entering
+    torch.cuda.device() costs ~3 us per call, a third of a batch-1 call's host time (profiles/r02/v15_latency_batch1.json)."""
+    if device.index is None or device.index == torch.cuda.current_device():
+        return _NO_GUARD
+    return torch.cuda.device(device)
+
+
 def _require_cuda(*tensors):
     first = None
     for t in tensors:
@@ -165,7 +184,7 @@ def fk_jacobian_raw(topo, ee_link, table, q, want_pos=True, want_quat=True, want
         quat = torch.empty((B, 4), device=dev, dtype=torch.float32) if want_quat else None
         jlin = torch.empty((B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
         jang = torch.empty((B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib().drmb200_fk_jacobian(ctypes.byref(topo), ee_link, _ptr(table), _ptr(q), B, _ptr(pos), _ptr(quat),
                                        _ptr(jlin), _ptr(jang), _stream())
     _check(rc, "drmb200_fk_jacobian")
@@ -186,7 +205,7 @@ def fk_jacobian_multi_raw(topo, ee_links, table, q, want_pos=True, want_quat=Tru
         jlin = torch.empty((E, B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
         jang = torch.empty((E, B, 3, n), device=dev, dtype=torch.float32) if want_jac else None
     links = (ctypes.c_int32 * E)(*[int(l) for l in ee_links])
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib().drmb200_fk_jacobian_multi(ctypes.byref(topo), E, links, _ptr(table), _ptr(q), B, _ptr(pos), _ptr(quat),
                                              _ptr(jlin), _ptr(jang), _stream())
     _check(rc, "drmb200_fk_jacobian_multi")
@@ -198,7 +217,7 @@ def inverse_dynamics_raw(topo, table, q, qd, qdd, flags, out=None):
     q, qd, qdd = q.contiguous(), qd.contiguous(), qdd.contiguous()
     B, n = q.shape
     tau = out if out is not None else torch.empty((B, n), device=q.device, dtype=torch.float32)
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         rc = lib().drmb200_inverse_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B,
                                             flags, _ptr(tau), _stream())
     _check(rc, "drmb200_inverse_dynamics")
@@ -211,7 +230,7 @@ def forward_dynamics_raw(topo, table, q, qd, f, flags, out=None):
     q, qd, f = q.contiguous(), qd.contiguous(), f.contiguous()
     B, n = q.shape
     qdd = out if out is not None else torch.empty((B, n), device=q.device, dtype=torch.float32)
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         rc = lib().drmb200_forward_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B,
                                             flags, _ptr(qdd), _stream())
     _check(rc, "drmb200_forward_dynamics")
@@ -227,7 +246,7 @@ def kinematic_state_raw(topo, table, q, qd=None, want_poses=True, want_quats=Fal
     poses = torch.empty((N, 12, B), device=dev, dtype=torch.float32) if want_poses else None
     quats = torch.empty((N, 4, B), device=dev, dtype=torch.float32) if want_quats else None
     vels = torch.empty((N, 6, B), device=dev, dtype=torch.float32) if qd is not None else None
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib().drmb200_kinematic_state(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), B, _ptr(poses), _ptr(quats),
                                            _ptr(vels), _stream())
     _check(rc, "drmb200_kinematic_state")
@@ -242,7 +261,7 @@ def dynamic_state_raw(topo, table, q, qd, qdd, flags, want_tau=True):
     N, dev = topo.n_links, q.device
     tau = torch.empty((B, n), device=dev, dtype=torch.float32) if want_tau else None
     vels, accs, forces = (torch.empty((N, 6, B), device=dev, dtype=torch.float32) for _ in range(3))
-    with torch.cuda.device(dev):
+    with _on(dev):
         rc = lib().drmb200_dynamic_state(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B, flags, _ptr(tau),
                                          _ptr(vels), _ptr(accs), _ptr(forces), _stream())
     _check(rc, "drmb200_dynamic_state")
@@ -290,7 +309,7 @@ class BuildLinkTableFunction(torch.autograd.Function):
         raw = raw.contiguous()
         n_links = raw.shape[0]
         table = torch.empty((n_links, 28), device=raw.device, dtype=torch.float32)
-        with torch.cuda.device(raw.device):
+        with _on(raw.device):
             rc = lib().drmb200_build_link_table(_ptr(raw), n_links, _ptr(table), _stream())
         _check(rc, "drmb200_build_link_table")
         ctx.save_for_backward(raw)
@@ -302,7 +321,7 @@ class BuildLinkTableFunction(torch.autograd.Function):
         g_table = g_table.contiguous()
         _require_cuda(g_table)
         g_raw = torch.empty_like(raw)
-        with torch.cuda.device(raw.device):
+        with _on(raw.device):
             rc = lib().drmb200_build_link_table_backward(_ptr(raw), _ptr(g_table), raw.shape[0], _ptr(g_raw), _stream())
         _check(rc, "drmb200_build_link_table_backward")
         return g_raw
@@ -321,7 +340,7 @@ class FusedTableFunction(torch.autograd.Function):
         n_links = const_raw.shape[0]
         raw = torch.empty_like(const_raw)
         table = torch.empty((n_links, 28), device=flat.device, dtype=torch.float32)
-        with torch.cuda.device(flat.device):
+        with _on(flat.device):
             rc = lib().drmb200_build_link_table_fused(_ptr(const_raw), _ptr(flat), _ptr(src), _ptr(kind), _ptr(off), n_links,
                                                       _ptr(raw), _ptr(table), _stream())
         _check(rc, "drmb200_build_link_table_fused")
@@ -335,7 +354,7 @@ class FusedTableFunction(torch.autograd.Function):
         _require_cuda(g_table)
         g_flat = torch.empty_like(flat)
         scratch = torch.empty_like(raw)
-        with torch.cuda.device(flat.device):
+        with _on(flat.device):
             rc = lib().drmb200_build_link_table_fused_backward(_ptr(raw), _ptr(g_table), _ptr(flat), _ptr(src), _ptr(kind),
                                                                raw.shape[0], flat.numel(), _ptr(scratch), _ptr(g_flat),
                                                                _stream())
@@ -364,7 +383,7 @@ class FkJacobianFunction(torch.autograd.Function):
         q_grad = torch.empty_like(q) if need_q else None
         table_grad = torch.zeros_like(table) if need_table else None
         ws = _workspace(ctx.topo, B, q.device)
-        with torch.cuda.device(q.device):
+        with _on(q.device):
             rc = lib().drmb200_fk_jacobian_backward(ctypes.byref(ctx.topo), ctx.ee_link, _ptr(table), _ptr(q), B,
                                                     _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _ptr(q_grad),
                                                     _ptr(table_grad), _ptr(ws), _stream())
@@ -399,7 +418,7 @@ class FkJacobianMultiFunction(torch.autograd.Function):
                 continue
             _require_cuda(*g)
             q_grad_e = torch.empty_like(q) if need_q else None
-            with torch.cuda.device(q.device):
+            with _on(q.device):
                 rc = lib().drmb200_fk_jacobian_backward(ctypes.byref(ctx.topo), int(link), _ptr(table), _ptr(q), B,
                                                         _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), _ptr(g[3]), _ptr(q_grad_e),
                                                         _ptr(table_grad), _ptr(ws), _stream())
@@ -445,7 +464,7 @@ class AllLinksFkFunction(torch.autograd.Function):
             gq = None if g_quat is None else g_quat[link].contiguous()
             _require_cuda(gp, gq)
             q_grad_l = torch.empty_like(q) if need_q else None
-            with torch.cuda.device(q.device):
+            with _on(q.device):
                 rc = lib().drmb200_fk_jacobian_backward(ctypes.byref(ctx.topo), int(link), _ptr(table), _ptr(q), B, _ptr(gp),
                                                         _ptr(gq), None, None, _ptr(q_grad_l), _ptr(table_grad), _ptr(ws),
                                                         _stream())
@@ -481,7 +500,7 @@ class InverseDynamicsFunction(torch.autograd.Function):
         flags = ctx.flags
         if need[1] or need[2] or need[3] or not need[0]:
             flags &= ~INERTIAL_GRADS_ONLY                   # the single-sweep kernel only produces table columns
-        with torch.cuda.device(q.device):
+        with _on(q.device):
             rc = lib().drmb200_inverse_dynamics_backward(
                 ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B, flags, _ptr(g_tau), _ptr(q_grad), _ptr(qd_grad), _ptr(qdd_grad),
                 _ptr(table_grad), _ptr(ws), _stream())
@@ -513,7 +532,7 @@ class ForwardDynamicsFunction(torch.autograd.Function):
         f_grad = torch.empty_like(q) if need[3] else None
         nbytes = int(lib().drmb200_forward_dynamics_backward_workspace_bytes(ctypes.byref(ctx.topo), B))
         ws = torch.empty((nbytes + 3) // 4, device=q.device, dtype=torch.float32)
-        with torch.cuda.device(q.device):
+        with _on(q.device):
             rc = lib().drmb200_forward_dynamics_backward(
                 ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B, ctx.flags, _ptr(g_qdd), _ptr(q_grad), _ptr(qd_grad),
                 _ptr(f_grad), _ptr(table_grad), _ptr(ws), _stream())
@@ -527,7 +546,7 @@ def mass_matrix_raw(topo, table, q, out=None):
     q = q.contiguous()
     B, n = q.shape
     H = out if out is not None else torch.empty((B, n, n), device=q.device, dtype=torch.float32)
-    with torch.cuda.device(q.device):
+    with _on(q.device):
         rc = lib().drmb200_mass_matrix(ctypes.byref(topo), _ptr(table), _ptr(q), B, _ptr(H), _stream())
     _check(rc, "drmb200_mass_matrix")
     return H
@@ -561,7 +580,7 @@ class MassMatrixFunction(torch.autograd.Function):
         table_grad = torch.zeros_like(table) if need_table else None
         q_grad = torch.empty_like(qs) if need_q else None
         ws = _workspace(ctx.topo, n * B, q.device)
-        with torch.cuda.device(q.device):
+        with _on(q.device):
             rc = lib().drmb200_inverse_dynamics_backward(
                 ctypes.byref(ctx.topo), _ptr(table), _ptr(qs), _ptr(zeros), _ptr(qdd.view(n * B, n)), n * B, 0, _ptr(g_tau),
                 _ptr(q_grad), None, None, _ptr(table_grad), _ptr(ws), _stream())
