@@ -36,6 +36,7 @@ static const Option g_option_table[] = {
     {"tree_grid_cap", "DRMB200_TREE_GRID_CAP", 0},   // 9: multi-ee tree kernel: resident CTAs per SM, 0 = as many as fit
     {"tree_bufs", "DRMB200_TREE_BUFS", 1},       // 10: multi-ee tree kernel: output tiles per warp (1 or 2)
     {"rnea_fold", "DRMB200_RNEA_FOLD", 1},       // 11: inverse-dynamics kernel: fold fixed links into their movable ancestors (default)
+    {"rnea_tile", "DRMB200_RNEA_TILE", 0},       // 12: inverse-dynamics kernel: configurations per CTA, 64 / 128, 0 = by batch size
 };
 constexpr int N_OPTIONS = sizeof(g_option_table) / sizeof(g_option_table[0]);
 static std::atomic<int> g_options[N_OPTIONS];

@@ -466,9 +466,11 @@ int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     // "rnea_fold" (default on): walk only the movable links, fixed links folded into their movable ancestors at staging time
     const bool fold = cp->foldable && get_option(11) != 0;
     const TreeProgram* prog = fold ? &cp->red : &cp->full;
-    // tile: 64 for batches that would not fill two waves of 128-row CTAs (more, smaller CTAs balance the SMs and the
-    // shared-memory-limited residency is the same number of warps), and for models whose 128-row footprint is too big
-    int tile = (batch <= 148 * 1024) ? 64 : 128;
+    // tile: 128 amortises the table staging (heavier since it folds the fixed links) over twice the configurations:
+    // 13.4 against 11.9 G cfg/s at 65 536 per launch, 13.0 against 11.5 at 2^21 (Panda, profiles/r02); 64 only for batches
+    // that would leave SMs without a CTA, and for models whose 128-row footprint is too big
+    int tile = (batch < 32768) ? 64 : 128;
+    if (get_option(12) == 64 || get_option(12) == 128) tile = get_option(12);
     if ((size_t)RneaSmemLayout(128, prog->n_dofs, prog->n_links, prog->n_slots).total_floats * sizeof(float) > 110 * 1024) tile = 64;
     RneaArgs args;
     args.table = table; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
