@@ -546,6 +546,10 @@ int pdl_decide(cudaStream_t stream, const PdlRange* ins, int n_ins, const PdlRan
         log = &g_logs[g_log_clock++ & 15];
         *log = StreamLog();
         log->used = true; log->dev = dev; log->stream = stream;
+        // nothing is known about the FK launches that may still be in flight on this stream (first use, or its history
+        // was evicted by 16 other streams): this launch is an ordinary one -- it starts after everything before it on the
+        // stream has completed, so whatever was forgotten cannot matter to the launches that follow it
+        mode = 0;
     }
     if (mode == 2) {
         if (smem_share < 0.25) mode = 0;
