@@ -470,7 +470,7 @@ int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     // 13.4 against 11.9 G cfg/s at 65 536 per launch, 13.0 against 11.5 at 2^21 (Panda, profiles/r02); 64 only for batches
     // that would leave SMs without a CTA, and for models whose 128-row footprint is too big
     int tile = (batch < 32768) ? 64 : 128;
-    if (get_option(12) == 64 || get_option(12) == 128) tile = get_option(12);
+    if (get_option(12) == 64 || get_option(12) == 128) tile = get_option(12);      // 256 was measured too: 11.7 G cfg/s
     if ((size_t)RneaSmemLayout(128, prog->n_dofs, prog->n_links, prog->n_slots).total_floats * sizeof(float) > 110 * 1024) tile = 64;
     RneaArgs args;
     args.table = table; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
