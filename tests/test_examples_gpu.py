@@ -40,3 +40,11 @@ def test_learn_kinematics_of_toy():
     import learn_kinematics_of_toy as ex
     hist = ex.run(n_epochs=600, n_data=100, device="cuda:0")
     assert hist[-1] < 0.5 * hist[0]
+
+
+def test_learn_dynamics_iiwa_sharded_single_rank():
+    """The sharded-batch example (fused flat parameter, fused all-reduce + Adam kernel, one CUDA graph per iteration) on one
+    rank; tests/test_sharded_gpu.py covers the N >= 2 exchange."""
+    import learn_dynamics_iiwa_sharded as ex
+    hist = ex.run(n_iters=150, n_data=8192, log=lambda *_: None)
+    assert all(h == h for h in hist) and hist[-1] < 0.5 * hist[0]
