@@ -70,7 +70,9 @@ def bench_config(n_gpus):
             "urdf": "kuka_iiwa/urdf/iiwa7.urdf", "ee_link": EE_LINK, "batch_per_step_per_gpu": BATCH,
             "global_batch_per_step": BATCH * n_gpus,
             "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
-            "inputs": "q ~ U(joint limits), seeded per rank"}
+            "inputs": "q ~ U(joint limits), seeded per rank",
+            "l2_policy": f"GPU arm: inputs / outputs rotate over {ROTATE} distinct buffer sets "
+                         f"({ROTATE * BATCH * BYTES_PER_CONFIG / 1e6:.0f} MB) > the 126 MB L2, no launch finds its data in L2"}
 
 
 def measured_peak_gbs():
