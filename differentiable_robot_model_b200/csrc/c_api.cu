@@ -81,6 +81,10 @@ int inverse_dynamics_device(const drmb200_topology_t*, const float*, const float
                             int64_t, uint32_t, float*, cudaStream_t);
 int dynamic_state_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*, int64_t, uint32_t,
                          float*, float*, float*, float*, cudaStream_t);
+int64_t folded_table_rows(const drmb200_topology_t*);
+int fold_table_device(const drmb200_topology_t*, const float*, float*, cudaStream_t);
+int inverse_dynamics_prefolded_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*, int64_t,
+                                      uint32_t, float*, cudaStream_t);
 int inverse_dynamics_backward_device(const drmb200_topology_t*, const float*, const float*, const float*,
                                      const float*, int64_t, uint32_t, const float*, float*, float*, float*,
                                      float*, void*, cudaStream_t);
@@ -272,6 +276,18 @@ int drmb200_inverse_dynamics(const drmb200_topology_t* topo, const float* table,
                              const float* qdd, int64_t batch, uint32_t flags, float* tau, void* cuda_stream) {
     return drm::inverse_dynamics_device(topo, table, q, qd, qdd, batch, flags, tau,
                                         static_cast<cudaStream_t>(cuda_stream));
+}
+
+int64_t drmb200_folded_table_rows(const drmb200_topology_t* topo) { return drm::folded_table_rows(topo); }
+
+int drmb200_fold_link_table(const drmb200_topology_t* topo, const float* table, float* folded, void* cuda_stream) {
+    return drm::fold_table_device(topo, table, folded, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_inverse_dynamics_prefolded(const drmb200_topology_t* topo, const float* folded, const float* q, const float* qd,
+                                       const float* qdd, int64_t batch, uint32_t flags, float* tau, void* cuda_stream) {
+    return drm::inverse_dynamics_prefolded_device(topo, folded, q, qd, qdd, batch, flags, tau,
+                                                  static_cast<cudaStream_t>(cuda_stream));
 }
 
 int drmb200_dynamic_state(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,

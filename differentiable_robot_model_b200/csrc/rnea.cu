@@ -27,6 +27,7 @@
 //
 // Algorithmic HBM bytes per configuration: 12n in + 4n out = 16n (112 B at n = 7).  At roughly
 // 2 kflop per 7-DoF configuration the kernel is FP32-issue-bound, not HBM-bound.
+#include <cstdlib>
 #include <cstring>
 #include "drm_common.cuh"
 
@@ -117,8 +118,15 @@ rnea_kernel(const __grid_constant__ TreeProgram prog, const __grid_constant__ Fo
         coop_copy(s_qd, args.qd + tile_start * n, valid * n, vec_ok);
         coop_copy(s_qdd, args.qdd + tile_start * n, valid * n, vec_ok);
     }
-    if (FOLD) stage_folded_table(s_tab, s_link, args.table, fold, prog, T);      // s_link: scratch until the walk starts
-    else stage_canonical_table(s_tab, args.table, prog, T);
+    if (FOLD) {
+        if (fold.n_full == 0) {        // args.table already holds the folded canonical rows (drmb200_fold_link_table): plain copy
+            for (int i = tid; i < N * DRMB200_TABLE_STRIDE; i += T) s_tab[i] = __ldg(args.table + i);
+        } else {
+            stage_folded_table(s_tab, s_link, args.table, fold, prog, T);      // s_link: scratch until the walk starts
+        }
+    } else {
+        stage_canonical_table(s_tab, args.table, prog, T);
+    }
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
 
@@ -453,6 +461,67 @@ const CachedPrograms* cached_programs(const drmb200_topology_t* topo, int* rc_ou
     c.topo = *topo; c.valid = true;
     next ^= 1;
     return &c;
+}
+
+// The folded canonical table of a link table, once, for callers whose table does not change between launches (constant
+// models): staging it per CTA costs 13-15 % of the inverse-dynamics kernel (measured by skipping it: 15.7 against 13.6 G cfg/s
+// at 65 536 per launch), a plain copy of n_red x 28 floats costs nothing.  Output: [n_red, 28] canonical rows (row 0 unused).
+__global__ void __launch_bounds__(64)
+fold_table_kernel(const __grid_constant__ TreeProgram prog, const __grid_constant__ FoldProgram fold,
+                  const float* __restrict__ table, float* __restrict__ folded) {
+    extern __shared__ __align__(16) float fsm[];
+    float* s_tab = fsm;                                                    // [n_red][28]
+    float* scratch = fsm + fold.n_red * DRMB200_TABLE_STRIDE;              // [n_full][40]
+    for (int i = threadIdx.x; i < DRMB200_TABLE_STRIDE; i += 64) s_tab[i] = 0.f;
+    stage_folded_table(s_tab, scratch, table, fold, prog, 64);
+    for (int i = threadIdx.x; i < fold.n_red * DRMB200_TABLE_STRIDE; i += 64) folded[i] = s_tab[i];
+}
+
+int64_t folded_table_rows(const drmb200_topology_t* topo) {
+    int rc;
+    const CachedPrograms* cp = cached_programs(topo, &rc);
+    if (cp == nullptr) return rc;
+    return (cp->foldable && get_option(11) != 0) ? cp->fold.n_red : 0;
+}
+
+int fold_table_device(const drmb200_topology_t* topo, const float* table, float* folded, cudaStream_t stream) {
+    int rc;
+    const CachedPrograms* cp = cached_programs(topo, &rc);
+    if (cp == nullptr) return rc;
+    if (!cp->foldable) { set_error("this topology has no link behind a fixed joint to fold (drmb200_folded_table_rows() == 0)"); return DRMB200_EINVAL; }
+    if (table == nullptr || folded == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    const size_t smem = (size_t)(cp->fold.n_red * DRMB200_TABLE_STRIDE + cp->fold.n_full * 40) * sizeof(float);
+    fold_table_kernel<<<1, 64, smem, stream>>>(cp->red, cp->fold, table, folded);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("fold_table launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
+    count_launch();
+    return DRMB200_OK;
+}
+
+// inverse dynamics from a table folded beforehand (drmb200_fold_link_table)
+int inverse_dynamics_prefolded_device(const drmb200_topology_t* topo, const float* folded, const float* q, const float* qd,
+                                      const float* qdd, int64_t batch, uint32_t flags, float* tau, cudaStream_t stream) {
+    int rc;
+    const CachedPrograms* cp = cached_programs(topo, &rc);
+    if (cp == nullptr) return rc;
+    if (!cp->foldable) { set_error("this topology has no link behind a fixed joint to fold"); return DRMB200_EINVAL; }
+    if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
+    if (batch == 0 || cp->red.n_dofs == 0) return DRMB200_OK;
+    if (folded == nullptr || q == nullptr || qd == nullptr || qdd == nullptr || tau == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
+    const TreeProgram* prog = &cp->red;
+    int tile = (batch < 32768) ? 64 : 128;
+    if (get_option(12) == 64 || get_option(12) == 128) tile = get_option(12);
+    if ((size_t)RneaSmemLayout(128, prog->n_dofs, prog->n_links, prog->n_slots).total_floats * sizeof(float) > 110 * 1024) tile = 64;
+    RneaArgs args;
+    args.table = folded; args.q = q; args.qd = qd; args.qdd = qdd; args.tau = tau; args.batch = batch; args.flags = flags;
+    args.vels = args.accs = args.forces = nullptr;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    args.aligned = (al16(q) && al16(qd) && al16(qdd) && al16(tau)) ? 1 : 0;
+    FoldProgram pre = cp->fold;
+    pre.n_full = 0;                                       // the kernel's "rows are folded already" flag
+    const bool packed = get_option(4) != 0;
+    if (tile == 64) return packed ? launch_rnea<64, true, false, true>(*prog, pre, args, stream) : launch_rnea<64, false, false, true>(*prog, pre, args, stream);
+    return packed ? launch_rnea<128, true, false, true>(*prog, pre, args, stream) : launch_rnea<128, false, false, true>(*prog, pre, args, stream);
 }
 
 int inverse_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,

@@ -43,6 +43,10 @@ _SIGNATURES = {
     "drmb200_inverse_dynamics": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p,
                                                 _c_float_p, ctypes.c_int64, ctypes.c_uint32, _c_float_p,
                                                 ctypes.c_void_p]),
+    "drmb200_folded_table_rows": (ctypes.c_int64, [ctypes.POINTER(Topology)]),
+    "drmb200_fold_link_table": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, ctypes.c_void_p]),
+    "drmb200_inverse_dynamics_prefolded": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                          ctypes.c_int64, ctypes.c_uint32, _c_float_p, ctypes.c_void_p]),
     "drmb200_dynamic_state": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                              ctypes.c_int64, ctypes.c_uint32, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                              ctypes.c_void_p]),
@@ -212,14 +216,34 @@ def fk_jacobian_multi_raw(topo, ee_links, table, q, want_pos=True, want_quat=Tru
     return pos, quat, jlin, jang
 
 
-def inverse_dynamics_raw(topo, table, q, qd, qdd, flags, out=None):
-    _require_cuda(table, q, qd, qdd)
+def fold_link_table(topo, table):
+    """Folded canonical rows [n_red, 28] of a link table (drmb200_fold_link_table), or None if there is nothing to fold.
+    For tables that do not change between launches: drmb200_inverse_dynamics_prefolded reads them with a plain copy instead
+    of folding the fixed links once per CTA."""
+    _require_cuda(table)
+    rows = int(lib().drmb200_folded_table_rows(ctypes.byref(topo)))
+    if rows <= 0:
+        return None
+    folded = torch.empty((rows, 28), device=table.device, dtype=torch.float32)
+    with _on(table.device):
+        rc = lib().drmb200_fold_link_table(ctypes.byref(topo), _ptr(table.contiguous()), _ptr(folded), _stream())
+    _check(rc, "drmb200_fold_link_table")
+    return folded
+
+
+def inverse_dynamics_raw(topo, table, q, qd, qdd, flags, out=None, folded=None):
+    """tau [B, n].  `folded`: rows from fold_link_table(topo, table) for a table that has not changed since."""
+    _require_cuda(table, q, qd, qdd, folded)
     q, qd, qdd = q.contiguous(), qd.contiguous(), qdd.contiguous()
     B, n = q.shape
     tau = out if out is not None else torch.empty((B, n), device=q.device, dtype=torch.float32)
     with _on(q.device):
-        rc = lib().drmb200_inverse_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B,
-                                            flags, _ptr(tau), _stream())
+        if folded is not None:
+            rc = lib().drmb200_inverse_dynamics_prefolded(ctypes.byref(topo), _ptr(folded), _ptr(q), _ptr(qd), _ptr(qdd), B,
+                                                          flags & 3, _ptr(tau), _stream())
+        else:
+            rc = lib().drmb200_inverse_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B,
+                                                flags, _ptr(tau), _stream())
     _check(rc, "drmb200_inverse_dynamics")
     return tau
 
@@ -478,9 +502,9 @@ class InverseDynamicsFunction(torch.autograd.Function):
     """(table, q, qd, qdd) -> tau; analytic RNEA adjoint kernel."""
 
     @staticmethod
-    def forward(ctx, table, q, qd, qdd, topo, flags):
+    def forward(ctx, table, q, qd, qdd, topo, flags, folded=None):
         table, q, qd, qdd = table.contiguous(), q.contiguous(), qd.contiguous(), qdd.contiguous()
-        tau = inverse_dynamics_raw(topo, table, q, qd, qdd, flags)
+        tau = inverse_dynamics_raw(topo, table, q, qd, qdd, flags, folded=folded)
         ctx.save_for_backward(table, q, qd, qdd)
         ctx.topo, ctx.flags = topo, flags
         return tau
@@ -505,7 +529,7 @@ class InverseDynamicsFunction(torch.autograd.Function):
                 ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(qdd), B, flags, _ptr(g_tau), _ptr(q_grad), _ptr(qd_grad), _ptr(qdd_grad),
                 _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_inverse_dynamics_backward")
-        return table_grad, q_grad, qd_grad, qdd_grad, None, None
+        return table_grad, q_grad, qd_grad, qdd_grad, None, None, None
 
 
 class ForwardDynamicsFunction(torch.autograd.Function):

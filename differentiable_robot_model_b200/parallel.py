@@ -61,6 +61,7 @@ def broadcast_link_table(model, src: int = 0) -> torch.Tensor:
     if active:
         dist.broadcast(table, src=src)
     model._table_cache = table
+    model._folded_cache = None
     return table
 
 

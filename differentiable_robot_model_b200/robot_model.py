@@ -128,6 +128,7 @@ class DifferentiableRobotModel(torch.nn.Module):
         self._topology = compile_topology(self._bodies, self._parent_idx)
         self._kin_state = None
         self._table_cache = None
+        self._folded_cache = None
         self._has_learnable = None          # any of the six per-link attributes replaced by a torch.nn.Module
 
     # ------------------------------------------------------------------------------------------
@@ -150,7 +151,18 @@ class DifferentiableRobotModel(torch.nn.Module):
     def invalidate_link_table(self) -> None:
         """Drop the cached link table (call after editing a constant link parameter tensor in place)."""
         self._table_cache = None
+        self._folded_cache = None
         self._has_learnable = None
+
+    def _folded_table(self):
+        """Constant models only: the link table with the links behind fixed joints folded into their movable ancestors
+        (``drmb200_fold_link_table``), computed once; the inverse-dynamics kernel then skips its per-CTA folding."""
+        if self._any_learnable_module() or getattr(self, "_shared_table", None) is not None:
+            return None
+        if getattr(self, "_folded_cache", None) is None:
+            folded = engine.fold_link_table(self._topology, self._link_table())
+            self._folded_cache = folded if folded is not None else False
+        return self._folded_cache if self._folded_cache is not False else None
 
     def _any_learnable_module(self) -> bool:
         if self._has_learnable is None:
@@ -317,11 +329,12 @@ class DifferentiableRobotModel(torch.nn.Module):
         table = self._link_table()
         if not self._kinematic_params_learnable():
             flags |= engine.INERTIAL_GRADS_ONLY     # backward hint: only (I_o, mc, m, damping) columns can matter
+        folded = self._folded_table()                  # constant model: folded once instead of once per CTA
         if torch.is_grad_enabled() and (
             table.requires_grad or q.requires_grad or qd.requires_grad or qdd_des.requires_grad
         ):
-            return engine.InverseDynamicsFunction.apply(table, q, qd, qdd_des, self._topology, flags)
-        return engine.inverse_dynamics_raw(self._topology, table, q, qd, qdd_des, flags)
+            return engine.InverseDynamicsFunction.apply(table, q, qd, qdd_des, self._topology, flags, folded)
+        return engine.inverse_dynamics_raw(self._topology, table, q, qd, qdd_des, flags, folded=folded)
 
     @tensor_check
     def compute_non_linear_effects(

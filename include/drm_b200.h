@@ -153,6 +153,22 @@ int drmb200_inverse_dynamics(const drmb200_topology_t* topo,
                              int64_t batch, uint32_t flags, float* tau, void* cuda_stream);
 
 /*
+ * Folding once, for tables that do not change between launches (constant models).  drmb200_inverse_dynamics folds the links
+ * behind fixed joints into their movable ancestors while it stages the table ("rnea_fold"), once per CTA: 13-15 % of the
+ * kernel.  A caller whose table is constant can fold it ONCE:
+ *   drmb200_folded_table_rows   rows of the folded table (root + movable links), 0 if the topology has nothing to fold
+ *                               (or "rnea_fold" is off), < 0 on a bad topology;
+ *   drmb200_fold_link_table     table [n_links, 28] -> folded [rows, 28] (canonical joint frames; one tiny launch);
+ *   drmb200_inverse_dynamics_prefolded   the same kernel reading the folded rows with a plain copy; tau is bit-identical to
+ *                               drmb200_inverse_dynamics on the table the rows were folded from.
+ */
+int64_t drmb200_folded_table_rows(const drmb200_topology_t* topo);
+int drmb200_fold_link_table(const drmb200_topology_t* topo, const float* table, float* folded, void* cuda_stream);
+int drmb200_inverse_dynamics_prefolded(const drmb200_topology_t* topo,
+                                       const float* folded, const float* q, const float* qd, const float* qdd,
+                                       int64_t batch, uint32_t flags, float* tau, void* cuda_stream);
+
+/*
  * Inverse dynamics PLUS the per-link state the reference leaves behind in its body objects after
  * compute_inverse_dynamics (robot_model.py:183-193 `vel`, :262-277 `acc`, :284-301 `force`), in one launch.  Link-major,
  * component-major blocks (coalesced stores), natural link frames, row order (angular 3, linear 3):

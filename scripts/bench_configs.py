@@ -87,11 +87,16 @@ def bench_rnea(stem_cls, batch):
     sets = [tuple(t.to(DEV) for t in O.sample_inputs(robot, batch, seed=r)) for r in range(min(R, 8))]
     outs = [torch.empty(batch, n, device=DEV) for _ in sets]
     table, topo = m._link_table(), m._topology
-    ms = timed(lambda i: engine.inverse_dynamics_raw(topo, table, *sets[i % len(sets)], 3, out=outs[i % len(sets)]),
+    folded = engine.fold_link_table(topo, table)          # what model.compute_inverse_dynamics does for a constant model
+    ms = timed(lambda i: engine.inverse_dynamics_raw(topo, table, *sets[i % len(sets)], 3, out=outs[i % len(sets)], folded=folded),
                200 if batch <= (1 << 17) else 20)
+    ms_in_kernel = timed(lambda i: engine.inverse_dynamics_raw(topo, table, *sets[i % len(sets)], 3, out=outs[i % len(sets)]),
+                         200 if batch <= (1 << 17) else 20)
     by = 16 * n
     res = {"batch": batch, "ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
-           "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK}
+           "achieved_GBps": batch * by / ms / 1e6, "hbm_frac": batch * by / ms / 1e6 / PEAK,
+           "table": "folded once (drmb200_fold_link_table)" if folded is not None else "as given",
+           "configs_per_s_folding_in_the_kernel": batch / ms_in_kernel * 1e3}
     if batch <= 65536 and engine.lib().drmb200_set_option is not None and os.environ.get("DRMB200_SKIP_CPU") is None:
         # CPU beside it, same box: scalar C port on all cores and the torch port (bounded samples)
         import time

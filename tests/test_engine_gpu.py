@@ -468,3 +468,22 @@ def test_folding_fixed_links_does_not_change_mass_matrix_or_forward_dynamics(ste
     for a, b, what in zip(out[1], out[0], ("H", "qdd")):
         scale = float(b.abs().max())
         assert_close(a.cpu().numpy() / scale, b.cpu().numpy() / scale, rtol=2e-5, atol=5e-6, what=f"{stem} {what} folded vs every link")
+
+
+@pytest.mark.parametrize("stem", ["iiwa7", "panda_no_gripper", "allegro_hand_description_left", "iiwa7_allegro", "jaco"])
+def test_prefolded_table_gives_the_same_torques_bit_for_bit(stem):
+    """A constant model folds its table ONCE (drmb200_fold_link_table) and launches drmb200_inverse_dynamics_prefolded; the
+    kernel then copies the rows instead of folding them per CTA: same arithmetic, same bits."""
+    m = gpu_model(stem)
+    robot = O.load_robot(urdf_path(stem), torch.float32)
+    for batch in (37, 4099, 40000):
+        q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, batch, seed=batch))
+        folded = engine.fold_link_table(m._topology, m._link_table())
+        assert folded is not None and folded.shape[1] == 28
+        a = engine.inverse_dynamics_raw(m._topology, m._link_table(), q, qd, qdd, 3)
+        b = engine.inverse_dynamics_raw(m._topology, m._link_table(), q, qd, qdd, 3, folded=folded)
+        assert torch.equal(a, b)
+        assert torch.equal(m.compute_inverse_dynamics(q, qd, qdd), a)          # the model takes the prefolded path by itself
+    launches = engine.launch_count()
+    m.compute_inverse_dynamics(q, qd, qdd)
+    assert engine.launch_count() - launches == 1                               # folded once, not per call
