@@ -221,8 +221,13 @@ aba_kernel(const __grid_constant__ TreeProgram prog, const __grid_constant__ Fol
     }
     // fold.n_red > 0: fixed links folded into their movable ancestors, prog is the reduced tree (drm_common.cuh): a fixed
     // joint has S = 0, so its articulated inertia and bias force pass to the parent through a constant transform -- the fold
-    if (fold.n_red > 0) stage_folded_table(s_tab, s_link, args.table, fold, prog, T);
-    else stage_canonical_table(s_tab, args.table, prog, T);
+    if (fold.n_red > 0 && fold.n_full == 0) {                // args.table holds rows folded beforehand (drmb200_fold_link_table)
+        for (int i = tid; i < N * DRMB200_TABLE_STRIDE; i += T) s_tab[i] = __ldg(args.table + i);
+    } else if (fold.n_red > 0) {
+        stage_folded_table(s_tab, s_link, args.table, fold, prog, T);
+    } else {
+        stage_canonical_table(s_tab, args.table, prog, T);
+    }
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
 
@@ -430,15 +435,18 @@ static int launch_aba(const TreeProgram& prog, const FoldProgram& fold, const Ab
     return DRMB200_OK;
 }
 
-int forward_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
-                            const float* f, int64_t batch, uint32_t flags, float* qdd, cudaStream_t stream) {
+static int forward_dynamics_device_impl(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                                       const float* f, int64_t batch, uint32_t flags, float* qdd, cudaStream_t stream,
+                                       bool prefolded) {
     int rc;
     const CachedPrograms* cp = cached_programs(topo, &rc);
     if (cp == nullptr) return rc;
-    const bool folded = cp->foldable && get_option(11) != 0;      // "rnea_fold"
+    if (prefolded && !cp->foldable) { set_error("this topology has no link behind a fixed joint to fold"); return DRMB200_EINVAL; }
+    const bool folded = prefolded || (cp->foldable && get_option(11) != 0);      // "rnea_fold"
     const TreeProgram& prog = folded ? cp->red : cp->full;
     FoldProgram fold = cp->fold;
     if (!folded) fold.n_red = 0;
+    if (prefolded) fold.n_full = 0;                     // `table` holds the rows of drmb200_fold_link_table
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
     if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr || qd == nullptr || f == nullptr || qdd == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
@@ -454,6 +462,15 @@ int forward_dynamics_device(const drmb200_topology_t* topo, const float* table, 
     const size_t smem_bytes = bytes_of(tile);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
     return tile == 64 ? launch_aba<64>(prog, fold, args, smem_bytes, stream) : launch_aba<32>(prog, fold, args, smem_bytes, stream);
+}
+
+int forward_dynamics_device(const drmb200_topology_t* topo, const float* table, const float* q, const float* qd,
+                            const float* f, int64_t batch, uint32_t flags, float* qdd, cudaStream_t stream) {
+    return forward_dynamics_device_impl(topo, table, q, qd, f, batch, flags, qdd, stream, false);
+}
+int forward_dynamics_prefolded_device(const drmb200_topology_t* topo, const float* folded, const float* q, const float* qd,
+                                      const float* f, int64_t batch, uint32_t flags, float* qdd, cudaStream_t stream) {
+    return forward_dynamics_device_impl(topo, folded, q, qd, f, batch, flags, qdd, stream, true);
 }
 
 }  // namespace drm

@@ -81,6 +81,9 @@ int inverse_dynamics_device(const drmb200_topology_t*, const float*, const float
                             int64_t, uint32_t, float*, cudaStream_t);
 int dynamic_state_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*, int64_t, uint32_t,
                          float*, float*, float*, float*, cudaStream_t);
+int mass_matrix_prefolded_device(const drmb200_topology_t*, const float*, const float*, int64_t, float*, cudaStream_t);
+int forward_dynamics_prefolded_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*, int64_t,
+                                      uint32_t, float*, cudaStream_t);
 int64_t folded_table_rows(const drmb200_topology_t*);
 int fold_table_device(const drmb200_topology_t*, const float*, float*, cudaStream_t);
 int inverse_dynamics_prefolded_device(const drmb200_topology_t*, const float*, const float*, const float*, const float*, int64_t,
@@ -287,6 +290,17 @@ int drmb200_fold_link_table(const drmb200_topology_t* topo, const float* table, 
 int drmb200_inverse_dynamics_prefolded(const drmb200_topology_t* topo, const float* folded, const float* q, const float* qd,
                                        const float* qdd, int64_t batch, uint32_t flags, float* tau, void* cuda_stream) {
     return drm::inverse_dynamics_prefolded_device(topo, folded, q, qd, qdd, batch, flags, tau,
+                                                  static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_mass_matrix_prefolded(const drmb200_topology_t* topo, const float* folded, const float* q, int64_t batch, float* H,
+                                  void* cuda_stream) {
+    return drm::mass_matrix_prefolded_device(topo, folded, q, batch, H, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int drmb200_forward_dynamics_prefolded(const drmb200_topology_t* topo, const float* folded, const float* q, const float* qd,
+                                       const float* f, int64_t batch, uint32_t flags, float* qdd, void* cuda_stream) {
+    return drm::forward_dynamics_prefolded_device(topo, folded, q, qd, f, batch, flags, qdd,
                                                   static_cast<cudaStream_t>(cuda_stream));
 }
 

@@ -73,8 +73,13 @@ mass_matrix_kernel(const __grid_constant__ TreeProgram prog, const __grid_consta
         coop_copy(s_q, args.q + tile_start * n, valid * n, vec_ok);
     }
     // fold.n_red > 0: fixed links folded into their movable ancestors, prog is the reduced tree (drm_common.cuh)
-    if (fold.n_red > 0) stage_folded_table(s_tab, s_link, args.table, fold, prog, T);
-    else stage_canonical_table(s_tab, args.table, prog, T);
+    if (fold.n_red > 0 && fold.n_full == 0) {                // args.table holds rows folded beforehand (drmb200_fold_link_table)
+        for (int i = tid; i < N * DRMB200_TABLE_STRIDE; i += T) s_tab[i] = __ldg(args.table + i);
+    } else if (fold.n_red > 0) {
+        stage_folded_table(s_tab, s_link, args.table, fold, prog, T);
+    } else {
+        stage_canonical_table(s_tab, args.table, prog, T);
+    }
     __syncthreads();
     if (bulk) mbar_wait(&mbar, 0);
 
@@ -178,16 +183,19 @@ static int launch_mm(const TreeProgram& prog, const FoldProgram& fold, const MmA
     return DRMB200_OK;
 }
 
-int mass_matrix_device(const drmb200_topology_t* topo, const float* table, const float* q, int64_t batch, float* H,
-                       cudaStream_t stream) {
+// prefolded: `table` holds the rows of drmb200_fold_link_table (constant models fold once instead of once per CTA)
+int mass_matrix_device_impl(const drmb200_topology_t* topo, const float* table, const float* q, int64_t batch, float* H,
+                            cudaStream_t stream, bool prefolded) {
     int rc;
     const CachedPrograms* cp = cached_programs(topo, &rc);
     if (cp == nullptr) return rc;
+    if (prefolded && !cp->foldable) { set_error("this topology has no link behind a fixed joint to fold"); return DRMB200_EINVAL; }
     // "rnea_fold": walk only the movable links (fixed links folded into their movable ancestors while the table is staged)
-    const bool folded = cp->foldable && get_option(11) != 0;
+    const bool folded = prefolded || (cp->foldable && get_option(11) != 0);
     const TreeProgram& prog = folded ? cp->red : cp->full;
     FoldProgram fold = cp->fold;
     if (!folded) fold.n_red = 0;                        // the kernel's "no folding" flag
+    if (prefolded) fold.n_full = 0;                     // ... and its "rows are folded already" flag
     if (batch < 0) { set_error("batch=%lld < 0", (long long)batch); return DRMB200_EINVAL; }
     if (batch == 0 || prog.n_dofs == 0) return DRMB200_OK;
     if (table == nullptr || q == nullptr || H == nullptr) { set_error("null pointer argument"); return DRMB200_EINVAL; }
@@ -200,6 +208,14 @@ int mass_matrix_device(const drmb200_topology_t* topo, const float* table, const
     const size_t smem_bytes = bytes_of(tile);
     if (smem_bytes > 227 * 1024) { set_error("model needs %zu B of shared memory per CTA (> 227 KB)", smem_bytes); return DRMB200_ELIMIT; }
     return tile == 64 ? launch_mm<64>(prog, fold, args, smem_bytes, stream) : launch_mm<32>(prog, fold, args, smem_bytes, stream);
+}
+
+int mass_matrix_device(const drmb200_topology_t* topo, const float* table, const float* q, int64_t batch, float* H, cudaStream_t stream) {
+    return mass_matrix_device_impl(topo, table, q, batch, H, stream, false);
+}
+int mass_matrix_prefolded_device(const drmb200_topology_t* topo, const float* folded, const float* q, int64_t batch, float* H,
+                                 cudaStream_t stream) {
+    return mass_matrix_device_impl(topo, folded, q, batch, H, stream, true);
 }
 
 }  // namespace drm

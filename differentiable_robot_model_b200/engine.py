@@ -47,6 +47,10 @@ _SIGNATURES = {
     "drmb200_fold_link_table": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, ctypes.c_void_p]),
     "drmb200_inverse_dynamics_prefolded": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                                           ctypes.c_int64, ctypes.c_uint32, _c_float_p, ctypes.c_void_p]),
+    "drmb200_mass_matrix_prefolded": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, ctypes.c_int64, _c_float_p,
+                                                     ctypes.c_void_p]),
+    "drmb200_forward_dynamics_prefolded": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, _c_float_p,
+                                                          ctypes.c_int64, ctypes.c_uint32, _c_float_p, ctypes.c_void_p]),
     "drmb200_dynamic_state": (ctypes.c_int, [ctypes.POINTER(Topology), _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                              ctypes.c_int64, ctypes.c_uint32, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                              ctypes.c_void_p]),
@@ -248,15 +252,19 @@ def inverse_dynamics_raw(topo, table, q, qd, qdd, flags, out=None, folded=None):
     return tau
 
 
-def forward_dynamics_raw(topo, table, q, qd, f, flags, out=None):
-    """Articulated-body algorithm, one launch (drmb200_forward_dynamics)."""
-    _require_cuda(table, q, qd, f)
+def forward_dynamics_raw(topo, table, q, qd, f, flags, out=None, folded=None):
+    """Articulated-body algorithm, one launch (drmb200_forward_dynamics; `folded`: rows of fold_link_table for an unchanged table)."""
+    _require_cuda(table, q, qd, f, folded)
     q, qd, f = q.contiguous(), qd.contiguous(), f.contiguous()
     B, n = q.shape
     qdd = out if out is not None else torch.empty((B, n), device=q.device, dtype=torch.float32)
     with _on(q.device):
-        rc = lib().drmb200_forward_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B,
-                                            flags, _ptr(qdd), _stream())
+        if folded is not None:
+            rc = lib().drmb200_forward_dynamics_prefolded(ctypes.byref(topo), _ptr(folded), _ptr(q), _ptr(qd), _ptr(f), B,
+                                                          flags, _ptr(qdd), _stream())
+        else:
+            rc = lib().drmb200_forward_dynamics(ctypes.byref(topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B,
+                                                flags, _ptr(qdd), _stream())
     _check(rc, "drmb200_forward_dynamics")
     return qdd
 
@@ -536,9 +544,9 @@ class ForwardDynamicsFunction(torch.autograd.Function):
     """(table, q, qd, f) -> qdd; articulated-body kernel forward, analytic adjoint kernel backward."""
 
     @staticmethod
-    def forward(ctx, table, q, qd, f, topo, flags):
+    def forward(ctx, table, q, qd, f, topo, flags, folded=None):
         table, q, qd, f = table.contiguous(), q.contiguous(), qd.contiguous(), f.contiguous()
-        qdd = forward_dynamics_raw(topo, table, q, qd, f, flags)
+        qdd = forward_dynamics_raw(topo, table, q, qd, f, flags, folded=folded)
         ctx.save_for_backward(table, q, qd, f)
         ctx.topo, ctx.flags = topo, flags
         return qdd
@@ -561,17 +569,20 @@ class ForwardDynamicsFunction(torch.autograd.Function):
                 ctypes.byref(ctx.topo), _ptr(table), _ptr(q), _ptr(qd), _ptr(f), B, ctx.flags, _ptr(g_qdd), _ptr(q_grad), _ptr(qd_grad),
                 _ptr(f_grad), _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_forward_dynamics_backward")
-        return table_grad, q_grad, qd_grad, f_grad, None, None
+        return table_grad, q_grad, qd_grad, f_grad, None, None, None
 
 
-def mass_matrix_raw(topo, table, q, out=None):
-    """Joint-space inertia matrix [B, n, n], one launch (drmb200_mass_matrix)."""
-    _require_cuda(table, q)
+def mass_matrix_raw(topo, table, q, out=None, folded=None):
+    """Joint-space inertia matrix [B, n, n], one launch (drmb200_mass_matrix; `folded`: rows of fold_link_table)."""
+    _require_cuda(table, q, folded)
     q = q.contiguous()
     B, n = q.shape
     H = out if out is not None else torch.empty((B, n, n), device=q.device, dtype=torch.float32)
     with _on(q.device):
-        rc = lib().drmb200_mass_matrix(ctypes.byref(topo), _ptr(table), _ptr(q), B, _ptr(H), _stream())
+        if folded is not None:
+            rc = lib().drmb200_mass_matrix_prefolded(ctypes.byref(topo), _ptr(folded), _ptr(q), B, _ptr(H), _stream())
+        else:
+            rc = lib().drmb200_mass_matrix(ctypes.byref(topo), _ptr(table), _ptr(q), B, _ptr(H), _stream())
     _check(rc, "drmb200_mass_matrix")
     return H
 
@@ -582,9 +593,9 @@ class MassMatrixFunction(torch.autograd.Function):
     kernel over the n stacked unit-acceleration batches (q_grad summed over the stack, table_grad as is)."""
 
     @staticmethod
-    def forward(ctx, table, q, topo):
+    def forward(ctx, table, q, topo, folded=None):
         table, q = table.contiguous(), q.contiguous()
-        H = mass_matrix_raw(topo, table, q)
+        H = mass_matrix_raw(topo, table, q, folded=folded)
         ctx.save_for_backward(table, q)
         ctx.topo = topo
         return H
@@ -609,4 +620,4 @@ class MassMatrixFunction(torch.autograd.Function):
                 ctypes.byref(ctx.topo), _ptr(table), _ptr(qs), _ptr(zeros), _ptr(qdd.view(n * B, n)), n * B, 0, _ptr(g_tau),
                 _ptr(q_grad), None, None, _ptr(table_grad), _ptr(ws), _stream())
         _check(rc, "drmb200_inverse_dynamics_backward")
-        return table_grad, (q_grad.view(n, B, n).sum(0) if need_q else None), None
+        return table_grad, (q_grad.view(n, B, n).sum(0) if need_q else None), None, None

@@ -366,7 +366,7 @@ class DifferentiableRobotModel(torch.nn.Module):
         therefore do not change the result, exactly as in the reference up to its fp32 cancellation noise.
         Differentiable w.r.t. q and every learnable link parameter (RNEA adjoint kernel over the stacked columns)."""
         assert q.shape[1] == self._n_dofs
-        return engine.MassMatrixFunction.apply(self._link_table(), q, self._topology)
+        return engine.MassMatrixFunction.apply(self._link_table(), q, self._topology, self._folded_table())
 
     @tensor_check
     def compute_lagrangian_inertia_matrix_stacked(
@@ -403,7 +403,7 @@ class DifferentiableRobotModel(torch.nn.Module):
         this does not overwrite the caller's ``f`` when ``use_damping`` is set (``robot_model.py:521``)."""
         self._check_q(q, qd, f)
         flags = (engine.GRAVITY if include_gravity else 0) | (engine.DAMPING if use_damping else 0)
-        return engine.ForwardDynamicsFunction.apply(self._link_table(), q, qd, f, self._topology, flags)
+        return engine.ForwardDynamicsFunction.apply(self._link_table(), q, qd, f, self._topology, flags, self._folded_table())
 
     @tensor_check
     def compute_forward_dynamics_crba(

@@ -167,6 +167,12 @@ int drmb200_fold_link_table(const drmb200_topology_t* topo, const float* table, 
 int drmb200_inverse_dynamics_prefolded(const drmb200_topology_t* topo,
                                        const float* folded, const float* q, const float* qd, const float* qdd,
                                        int64_t batch, uint32_t flags, float* tau, void* cuda_stream);
+/* the mass-matrix and articulated-body kernels fold the same way; the same rows serve them */
+int drmb200_mass_matrix_prefolded(const drmb200_topology_t* topo, const float* folded, const float* q, int64_t batch,
+                                  float* H, void* cuda_stream);
+int drmb200_forward_dynamics_prefolded(const drmb200_topology_t* topo,
+                                       const float* folded, const float* q, const float* qd, const float* f,
+                                       int64_t batch, uint32_t flags, float* qdd, void* cuda_stream);
 
 /*
  * Inverse dynamics PLUS the per-link state the reference leaves behind in its body objects after
