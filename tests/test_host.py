@@ -249,3 +249,36 @@ def test_table_staging_permutation_matches_its_definition(tmp_path):
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout
     assert "all 49" in out.stdout
+
+
+def test_fused_parameter_map_reproduces_the_per_module_raw_rows():
+    """link_table.FusedLinkParameters (one flat Parameter for all learnable link parameters): applying its
+    (src, kind, off) map to the flat vector on the CPU gives exactly the raw rows the per-module path gathers, for
+    identity (UnconstrainedScalar / UnconstrainedTensor) and squared (PositiveScalar) parametrisations; modules on
+    fixed-joint origins feed nothing; the modules' own Parameters become views of the flat storage."""
+    from differentiable_robot_model_b200.link_table import FusedLinkParameters, gather_raw_parameters
+    from differentiable_robot_model_b200.rigid_body_params import PositiveScalar, UnconstrainedScalar
+    torch.manual_seed(0)
+    m = drm.DifferentiableKUKAiiwa(device="cpu")
+    m.make_link_param_learnable("iiwa_link_1", "mass", PositiveScalar(min_val=0.5))
+    m.make_link_param_learnable("iiwa_link_3", "com", UnconstrainedTensor(dim1=1, dim2=3))
+    m.make_link_param_learnable("iiwa_link_3", "inertia_mat", UnconstrainedTensor(dim1=3, dim2=3))
+    m.make_link_param_learnable("iiwa_link_5", "joint_damping", UnconstrainedScalar())
+    m.make_link_param_learnable("iiwa_link_2", "trans", UnconstrainedTensor(dim1=1, dim2=3))
+    m.make_link_param_learnable("iiwa_link_ee", "trans", UnconstrainedTensor(dim1=1, dim2=3))      # fixed joint: frozen
+    want = gather_raw_parameters(m._bodies, torch.device("cpu")).detach().clone()
+    fused = FusedLinkParameters(m._bodies, torch.device("cpu"))
+    flat = fused.flat.detach()
+    assert flat.numel() == 1 + 3 + 9 + 1 + 3 + 3
+    src, kind, off = fused.src.long(), fused.kind, fused.off
+    vals = torch.where(kind == 1, flat[src.clamp_min(0)] ** 2 + off, flat[src.clamp_min(0)])
+    raw = torch.where(src >= 0, vals, fused.const_raw.reshape(-1)).reshape(want.shape)
+    assert torch.equal(raw, want)
+    assert int((src >= 0).sum()) == flat.numel() - 3                    # the fixed link's trans feeds nothing
+    # the modules' Parameters alias the flat vector: an optimiser step on `flat` is visible through the modules
+    with torch.no_grad():
+        fused.flat.add_(1.0)
+    com = m._bodies[3].inertia.com.param
+    start = (com.data_ptr() - fused.flat.data_ptr()) // 4
+    assert 0 <= start <= flat.numel() - 3 and torch.equal(com.detach().reshape(-1), fused.flat.detach()[start:start + 3])
+    assert all(not p.requires_grad for n, p in m.named_parameters())
