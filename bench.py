@@ -527,6 +527,9 @@ def main():
                     "allreduce_scalars_per_step": c5["allreduce_scalars"], "step": c5["step"], "final_loss_rank0": c5["final_loss"],
                     "ms_per_step_with_nccl_allreduce_and_torch_adam_this_rank": c5["ms_per_step_nccl_allreduce_torch_adam"]},
                 "timing": "median over repetitions per rank, max over ranks; weak scaling (fixed per-GPU shard)"}
+            if world == 1:                                   # BASELINE config 3 is a single-GPU config
+                c3 = bench_sharded.config3(dev, barrier)
+                result["sharded_configs"]["config3_panda_inverse_dynamics_single_gpu"] = c3
         except Exception as exc:                              # report, do not hide
             result["sharded_configs"] = {"error": f"{type(exc).__name__}: {exc}"}
 

@@ -47,6 +47,51 @@ def _median_region_ms(stream, replay, reps, barrier):
     return statistics.median(out)
 
 
+def config3(dev, barrier, batch=65536, steps=64, reps=5):
+    """BASELINE config 3 (single GPU): Franka Panda inverse dynamics (RNEA, gravity + damping), 65 536 per launch, four
+    independent launches in flight (graph branches), inputs rotated over buffer sets larger than L2.  The model is constant,
+    so its table is folded once (drmb200_fold_link_table) like model.compute_inverse_dynamics does by itself."""
+    m = drm.DifferentiableFrankaPanda(device=dev)
+    table, topo = m._link_table(), m._topology
+    folded = engine.fold_link_table(topo, table)
+    n = m._n_dofs
+    R = 24                                                 # 24 x 7.3 MB > L2
+    sets = [sample(m, batch, 300 + r, dev) for r in range(R)]
+    outs = [torch.empty(batch, n, device=dev) for _ in range(R)]
+    stream = torch.cuda.Stream(device=dev)
+    side = [torch.cuda.Stream(device=dev) for _ in range(3)]
+
+    def step(i):
+        engine.inverse_dynamics_raw(topo, table, *sets[i % R], 3, out=outs[i % R], folded=folded)
+
+    with torch.cuda.stream(stream):
+        for i in range(4):
+            step(i)
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            fork = torch.cuda.Event()
+            fork.record(stream)
+            for s in side:
+                s.wait_event(fork)
+            for i in range(steps):
+                if i % 4 == 0:
+                    step(i)
+                else:
+                    with torch.cuda.stream(side[i % 4 - 1]):
+                        step(i)
+            for s in side:
+                j = torch.cuda.Event()
+                j.record(s)
+                stream.wait_event(j)
+        g.replay()
+        stream.synchronize()
+        ms = _median_region_ms(stream, g.replay, reps, barrier) / steps
+    return {"batch_per_launch": batch, "ms_per_launch": ms, "configs_per_s": batch / (ms * 1e-3), "algorithmic_bytes_per_config": 16 * n,
+            "table": "folded once" if folded is not None else "as given", "launch": "CUDA graph, 4 branches", "steps_per_region": steps,
+            "reps": reps}
+
+
 def config4(dev, rank, barrier, per_gpu=32768, steps=64, reps=5):
     """-> {fused_ms_per_step, per_tip_ms_per_step (4 launches)} on this rank's shard."""
     m = drm.DifferentiableRobotModel(os.path.join(drm.robot_model.robot_description_folder, ALLEGRO), "allegro", device=dev)
@@ -163,4 +208,5 @@ if __name__ == "__main__":
     import json
     d = torch.device("cuda", 0)
     torch.cuda.set_device(d)
-    print(json.dumps({"config4": config4(d, 0, torch.cuda.synchronize), "config5": config5(d, 0, 1, None, torch.cuda.synchronize)}))
+    print(json.dumps({"config3": config3(d, torch.cuda.synchronize), "config4": config4(d, 0, torch.cuda.synchronize),
+                      "config5": config5(d, 0, 1, None, torch.cuda.synchronize)}))
