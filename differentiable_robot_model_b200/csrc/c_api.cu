@@ -37,6 +37,7 @@ static const Option g_option_table[] = {
     {"tree_bufs", "DRMB200_TREE_BUFS", 1},       // 10: multi-ee tree kernel: output tiles per warp (1 or 2)
     {"rnea_fold", "DRMB200_RNEA_FOLD", 1},       // 11: inverse-dynamics kernel: fold fixed links into their movable ancestors (default)
     {"rnea_tile", "DRMB200_RNEA_TILE", 0},       // 12: inverse-dynamics kernel: configurations per CTA, 64 / 128, 0 = by batch size
+    {"rnea_bwd_chain", "DRMB200_RNEA_BWD_CHAIN", 1},   // 13: inverse-dynamics adjoint of serial chains: 1 = two-sweep kernel (default), 0 = the general tree kernel
 };
 constexpr int N_OPTIONS = sizeof(g_option_table) / sizeof(g_option_table[0]);
 static std::atomic<int> g_options[N_OPTIONS];
@@ -247,6 +248,13 @@ int64_t drmb200_launch_count(void) { return drm::g_launches.load(); }
 int drmb200_set_option(const char* name, int value) {
     if (drm::set_option_by_name(name, value) == DRMB200_OK) return DRMB200_OK;
     drm::set_error("unknown option");
+    return DRMB200_EINVAL;
+}
+int drmb200_get_option(const char* name, int* value) {
+    if (name == nullptr || value == nullptr) { drm::set_error("null argument"); return DRMB200_EINVAL; }
+    for (int k = 0; k < drm::N_OPTIONS; ++k)
+        if (std::string(name) == drm::g_option_table[k].name) { *value = drm::get_option(k); return DRMB200_OK; }
+    drm::set_error("unknown option '%s'", name);
     return DRMB200_EINVAL;
 }
 

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "drmb200_last_error": (ctypes.c_char_p, []),
     "drmb200_launch_count": (ctypes.c_int64, []),
     "drmb200_set_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int]),
+    "drmb200_get_option": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]),
     "drmb200_fk_jacobian": (ctypes.c_int, [ctypes.POINTER(Topology), ctypes.c_int32, _c_float_p, _c_float_p,
                                            ctypes.c_int64, _c_float_p, _c_float_p, _c_float_p, _c_float_p,
                                            ctypes.c_void_p]),
@@ -175,6 +176,12 @@ def launch_count():
 
 def set_option(name, value):
     _check(lib().drmb200_set_option(name.encode(), int(value)), "drmb200_set_option")
+
+
+def get_option(name):
+    value = ctypes.c_int(0)
+    _check(lib().drmb200_get_option(name.encode(), ctypes.byref(value)), "drmb200_get_option")
+    return int(value.value)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -95,6 +95,8 @@ int64_t drmb200_launch_count(void);        /* kernels launched by this library s
  *   "rnea_packed": 1 = packed FP32x2 arithmetic in the inverse-dynamics kernel (default), 0 = scalar FFMA;
  *   "rnea_fold":  1 = the inverse-dynamics kernel walks only the movable links, links behind fixed joints are folded into
  *                 their nearest movable ancestor while the table is staged (default), 0 = one step per link like the reference;
+ *   "rnea_bwd_chain": drmb200_inverse_dynamics_backward on robots whose links form one serial chain (every link's parent is
+ *                 the link before it): 1 = the two-sweep adjoint kernel (default), 0 = the general tree kernel;
  *   "host_fused": drmb200_fk_jacobian_host on page-locked buffers: 1 = one launch whose TMA copies cross PCIe (default),
  *                 0 = staged H2D -> kernel -> D2H pipeline;
  *   "fk_pdl":     programmatic dependent launch of drmb200_fk_jacobian.  0 (default): ordinary stream-ordered launches.
@@ -106,6 +108,7 @@ int64_t drmb200_launch_count(void);        /* kernels launched by this library s
  *                 how many launches can be in flight).  Measured: 2.85 us instead of 6.8 us per stream-ordered launch
  *                 of 65 536 Kuka configurations.  1: wait before the first global read (A/B only, slower than 0). */
 int drmb200_set_option(const char* name, int value);
+int drmb200_get_option(const char* name, int* value);   /* the value in effect (environment / default / last set) */
 
 /*
  * FK (+ geometric Jacobian) of link `ee_link` for a batch of joint configurations.

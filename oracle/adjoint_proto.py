@@ -258,6 +258,137 @@ def inverse_dynamics_backward(table, parent, axis, dof, q, qd, qdd, g_tau, gravi
     return q_grad, qd_grad, qdd_grad, tg
 
 
+def inverse_dynamics_backward_chain(table, dof, q, qd, qdd, g_tau, gravity=True, damping=True):
+    """The same adjoint, restated the way csrc/backward_rnea_chain.cu evaluates it: TWO sweeps over a serial chain whose
+    rows are canonical (every movable axis is +z; parent of link i is link i - 1), nothing per link kept except (cos, sin).
+
+      sweep 1, root -> leaves: motion state and wrench adjoints lam, mu -- only to arrive at the last link's values;
+      sweep 2, leaves -> root: the state AND the wrench adjoints of link i - 1 re-derived from link i's (both recursions
+        are invertible), the body wrench recomputed from the state and accumulated on the way (f, n), the motion
+        adjoints, and every gradient.
+    M = F Rz(theta) is never formed: x -> Rz^T (F^T x) and x -> F (Rz x); with y = M^T x and adjoint ybar the joint-angle
+    gradient of that product is (ybar x y).z and its F-gradient x (Rz ybar)^T.
+    Returns (q_grad, qd_grad, qdd_grad, table_grad) like inverse_dynamics_backward (axis codes: 3 movable, 0 fixed)."""
+    B, n = q.shape
+    N = table.shape[0]
+    dt = q.dtype
+    cr = _skew_cross
+    zero = torch.zeros(B, 3, dtype=dt)
+    a_root = torch.tensor([0.0, 0.0, 9.81 if gravity else 0.0], dtype=dt).expand(B, 3)
+
+    def rotz(x, c, s):        # Rz x
+        return torch.stack([c * x[:, 0] - s * x[:, 1], c * x[:, 1] + s * x[:, 0], x[:, 2]], 1)
+
+    def rotzT(x, c, s):       # Rz^T x
+        return torch.stack([c * x[:, 0] + s * x[:, 1], c * x[:, 1] - s * x[:, 0], x[:, 2]], 1)
+
+    def cz(a, b):             # (a x b).z
+        return a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+
+    def col(x, k, i):
+        return x[:, k] if k >= 0 else torch.zeros(B, dtype=dt)
+
+    ez = torch.tensor([0.0, 0.0, 1.0], dtype=dt)
+    # ---- sweep 1 ----------------------------------------------------------------------------------
+    w, v, al, a, lam, mu = zero, zero, zero, a_root, zero, zero
+    keep = [None] * N
+    for i in range(1, N):
+        F, r = table[i, 0:9].reshape(3, 3), table[i, 9:12].expand(B, 3)
+        k = dof[i]
+        cs = torch.cos(q[:, k]) if k >= 0 else torch.ones(B, dtype=dt)
+        sn = torch.sin(q[:, k]) if k >= 0 else torch.zeros(B, dtype=dt)
+        qd_k, qdd_k, g_k = col(qd, k, i), col(qdd, k, i), col(g_tau, k, i)
+        wn = rotzT(w @ F, cs, sn)                         # F^T x == x @ F for row vectors
+        vn = rotzT((cr(w, r) + v) @ F, cs, sn)
+        aln = rotzT(al @ F, cs, sn)
+        an = rotzT((cr(al, r) + a) @ F, cs, sn)
+        wn = wn + qd_k[:, None] * ez
+        aln = aln + cr(wn, qd_k[:, None] * ez) + qdd_k[:, None] * ez
+        an = an + cr(vn, qd_k[:, None] * ez)
+        u = cr(lam, r) + mu
+        lam = rotzT(lam @ F, cs, sn) + g_k[:, None] * ez
+        mu = rotzT(u @ F, cs, sn)
+        w, v, al, a = wn, vn, aln, an
+        keep[i] = (cs, sn)
+
+    # ---- sweep 2 ----------------------------------------------------------------------------------
+    q_grad, qd_grad, qdd_grad = (torch.zeros(B, n, dtype=dt) for _ in range(3))
+    tg = torch.zeros(N, 28, dtype=dt)
+    c_wb, c_vb, c_alb, c_ab, carry_f, carry_n = zero, zero, zero, zero, zero, zero
+    for i in range(N - 1, 0, -1):
+        F, r = table[i, 0:9].reshape(3, 3), table[i, 9:12].expand(B, 3)
+        Io, mc, m, d = table[i, 12:21].reshape(3, 3), table[i, 21:24].expand(B, 3), table[i, 24], table[i, 25]
+        L, U = lam, mu
+        cs, sn = keep[i]
+        k = dof[i]
+        qd_k, qdd_k, g_k = col(qd, k, i), col(qdd, k, i), col(g_tau, k, i)
+        wJ = qd_k[:, None] * ez
+        # (a, b) the parent's state through the inverted recursion
+        tw = w - wJ
+        tal = al - cr(w, wJ) - qdd_k[:, None] * ez
+        apre = a - cr(v, wJ)
+        if i > 1:
+            wp, alp = rotz(tw, cs, sn) @ F.T, rotz(tal, cs, sn) @ F.T          # F x == x @ F^T
+            Xv, Xa = rotz(v, cs, sn) @ F.T, rotz(apre, cs, sn) @ F.T          # = wp x r + vp, alp x r + ap
+            vp, ap = Xv - cr(wp, r), Xa - cr(alp, r)
+            LP = rotz(L - g_k[:, None] * ez, cs, sn) @ F.T                    # lam_i = M^T lam_p + g_k e_z
+            u = rotz(U, cs, sn) @ F.T                                         # mu_i = M^T (lam_p x r + mu_p)
+            UP = u - cr(LP, r)
+        else:
+            wp, alp, Xv, Xa, vp, ap = zero, zero, zero, a_root, zero, a_root
+            LP, u, UP = zero, zero, zero
+        # (c) body wrench from the state, plus what the child handed up
+        Hl = m * v - cr(mc, w)
+        Ha = w @ Io.T + cr(mc, v)
+        Bl = m * a - cr(mc, al)
+        Ba = al @ Io.T + cr(mc, a)
+        f = Bl + cr(w, Hl) + carry_f
+        nn = Ba + cr(w, Ha) + cr(v, Hl) + carry_n
+        # (d) to the parent
+        Rf, Rn = rotz(f, cs, sn), rotz(nn, cs, sn)
+        fp = Rf @ F.T
+        carry_f, carry_n = fp, cr(r, fp) + Rn @ F.T
+        # (e) wrench-adjoint part
+        th = cz(nn, L) + cz(f, U)
+        Fbar = LP[:, :, None] * Rn[:, None, :] + u[:, :, None] * Rf[:, None, :]
+        rbar = cr(fp, LP)
+        qdv = torch.zeros(B, dtype=dt)
+        if k >= 0 and damping:
+            qdv = d * g_k
+            tg[i, 25] += (g_k * qd_k).sum()
+        # (f) body part of the motion adjoints
+        wb, vb, alb, ab = c_wb, c_vb, c_alb, c_ab
+        Hlb = cr(U, w) + cr(L, v)
+        Hab = cr(L, w)
+        alb = alb + cr(mc, U) + L @ Io
+        ab = ab + m * U + cr(L, mc)
+        wb = wb + cr(Hl, U) + cr(Ha, L) + cr(mc, Hlb) + Hab @ Io
+        vb = vb + cr(Hl, L) + m * Hlb + cr(Hab, mc)
+        tg[i, 24] += ((U * a).sum(1) + (Hlb * v).sum(1)).sum()
+        tg[i, 21:24] += (cr(U, al) + cr(a, L) + cr(Hlb, w) + cr(v, Hab)).sum(0)
+        tg[i, 12:21] += (L[:, :, None] * al[:, None, :] + Hab[:, :, None] * w[:, None, :]).sum(0).reshape(9)
+        # (g) kinematic part
+        vb = vb + cr(wJ, ab)
+        wb = wb + cr(wJ, alb)
+        wJb = cz(ab, v) + cz(alb, w) + wb[:, 2]
+        th = th + cz(ab, apre) + cz(alb, tal) + cz(vb, v) + cz(wb, w)
+        Rwb, Ralb, Rvb, Rab = rotz(wb, cs, sn), rotz(alb, cs, sn), rotz(vb, cs, sn), rotz(ab, cs, sn)
+        uw, ual, uv, ua = Rwb @ F.T, Ralb @ F.T, Rvb @ F.T, Rab @ F.T
+        c_vb, c_ab = uv, ua
+        c_wb, c_alb = uw + cr(r, uv), ual + cr(r, ua)
+        Fbar = Fbar + Xv[:, :, None] * Rvb[:, None, :] + Xa[:, :, None] * Rab[:, None, :] \
+            + wp[:, :, None] * Rwb[:, None, :] + alp[:, :, None] * Ralb[:, None, :]
+        rbar = rbar + cr(ua, alp) + cr(uv, wp)
+        if k >= 0:
+            q_grad[:, k] = th
+            qd_grad[:, k] = wJb + qdv
+            qdd_grad[:, k] = alb[:, 2]
+        tg[i, 0:9] += Fbar.sum(0).reshape(9)
+        tg[i, 9:12] += rbar.sum(0)
+        w, v, al, a, lam, mu = wp, vp, alp, ap, LP, UP
+    return q_grad, qd_grad, qdd_grad, tg
+
+
 # ------------------------------------------------------------------------------------------------
 # articulated-body forward dynamics (robot_model.py:488-624) and its adjoint
 # ------------------------------------------------------------------------------------------------

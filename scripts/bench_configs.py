@@ -270,16 +270,22 @@ def bench_backward_kernels(batch):
                                               P(g_ja), P(qg), P(tg) if with_table else None, P(ws), S())
         assert rc == 0
 
-    def id_bwd(flags, inputs):
+    qdg, qddg = torch.empty_like(q), torch.empty_like(q)
+
+    def id_bwd(flags, inputs, with_table=True):
         rc = lib.drmb200_inverse_dynamics_backward(ctypes.byref(topo), P(table), P(q), P(qd), P(qdd), batch, flags, P(g_tau),
-                                                   P(qg) if inputs else None, P(qg) if inputs else None,
-                                                   P(qg) if inputs else None, P(tg), P(ws), S())
+                                                   P(qg) if inputs else None, P(qdg) if inputs else None,
+                                                   P(qddg) if inputs else None, P(tg) if with_table else None, P(ws), S())
         assert rc == 0
 
     for name, fn, by in (("fk_jacobian_backward_q_only", lambda i: fk_bwd(False), 28 + 28 + 168 + 28),
                          ("fk_jacobian_backward_q_and_table", lambda i: fk_bwd(True), 28 + 28 + 168 + 28),
                          ("rnea_backward_full", lambda i: id_bwd(3, True), 28 * 7),
+                         ("rnea_backward_inputs_only", lambda i: id_bwd(3, True, False), 28 * 7),
+                         ("rnea_backward_full_tree_kernel", lambda i: id_bwd(3, True), 28 * 7),
+                         ("rnea_backward_inputs_only_tree_kernel", lambda i: id_bwd(3, True, False), 28 * 7),
                          ("rnea_backward_inertial_only", lambda i: id_bwd(3 | 4, False), 16 * 7)):
+        engine.set_option("rnea_bwd_chain", 0 if name.endswith("tree_kernel") else 1)
         ms = timed(fn, 20)
         out[name] = {"ms": ms, "configs_per_s": batch / ms * 1e3, "algorithmic_bytes_per_config": by,
                      "achieved_GBps": batch * by / ms / 1e6}
@@ -362,6 +368,10 @@ def main():
     out = {"peak_GBps": PEAK, "gpu": torch.cuda.get_device_name(0)}
     if os.environ.get("BENCH_ONLY") == "config5":
         out["config5_kuka_train_step"] = [bench_train_step(131072, fused=False), bench_train_step(131072, fused=True)]
+        print(json.dumps(out))
+        return
+    if os.environ.get("BENCH_ONLY") == "backward":
+        out["kuka_backward_kernels"] = [bench_backward_kernels(b) for b in (131072, 1 << 20)]
         print(json.dumps(out))
         return
     if os.environ.get("BENCH_ONLY") == "rnea":

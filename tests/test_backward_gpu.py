@@ -307,3 +307,53 @@ def test_training_step_replays_from_a_cuda_graph():
         got.append(float(loss))
     np.testing.assert_allclose(got, want, rtol=2e-4)
     assert got[-1] < got[0]
+
+
+@pytest.mark.parametrize("stem", ["iiwa7", "panda_no_gripper", "fetch_arm_no_gripper", "2link_robot"])
+@pytest.mark.parametrize("batch", [1, 63, 64, 130, 4099])
+def test_chain_adjoint_kernel_matches_the_tree_kernel(stem, batch):
+    """Serial chains take the two-sweep RNEA adjoint kernel (option rnea_bwd_chain, default on); every gradient must agree
+    with the general tree kernel: all gradients (learnable model), input gradients only (constant model), bulk-copy and
+    cooperative staging (inputs off 16-byte alignment), full and partial tiles."""
+    from differentiable_robot_model_b200 import engine
+
+    if engine.get_option("rnea_bwd_chain") == 0:
+        pytest.skip("the two-sweep kernel is switched off (DRMB200_RNEA_BWD_CHAIN=0)")
+    robot = O.load_robot(urdf_path(stem), torch.float32)
+    n = robot.n_dofs
+    q, qd, qdd = (t.to(DEV) for t in O.sample_inputs(robot, batch, seed=batch + 5))
+    G = torch.randn(batch, n, device=DEV)
+    learn, params = learnable_model(stem)
+    const = drm.DifferentiableRobotModel(urdf_path(stem), stem, device=DEV)
+
+    def shifted(x):                      # the same values at an address that is not a multiple of 16 bytes
+        buf = torch.empty(x.numel() + 1, device=DEV)
+        buf[1:].copy_(x.reshape(-1))
+        return buf[1:].view_as(x)
+
+    def run(model, unaligned, grav, damp):
+        for p in params.values():
+            p.grad = None
+        ins = [(shifted(t) if unaligned else t.clone()).requires_grad_(True) for t in (q, qd, qdd)]
+        tau = model.compute_inverse_dynamics(*ins, include_gravity=grav, use_damping=damp)
+        (G * tau).sum().backward()
+        out = [t.grad.clone() for t in ins]
+        if model is learn:
+            out += [p.grad.clone() if p.grad is not None else torch.zeros_like(p) for p in params.values()]
+        return out
+
+    try:
+        for model in (learn, const):
+            for unaligned, grav, damp in ((False, True, True), (True, False, True), (False, True, False)):
+                engine.set_option("rnea_bwd_chain", 0)
+                want = run(model, unaligned, grav, damp)
+                engine.set_option("rnea_bwd_chain", 1)
+                before = engine.launch_count()
+                got = run(model, unaligned, grav, damp)
+                assert engine.launch_count() > before
+                scale = max(float(w.abs().max()) for w in want)
+                for i, (a, b) in enumerate(zip(got, want)):
+                    assert_close(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5 * max(scale, 1.0),
+                                 what=f"{stem} B={batch} learnable={model is learn} unaligned={unaligned} grad {i}")
+    finally:
+        engine.set_option("rnea_bwd_chain", 1)

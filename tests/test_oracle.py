@@ -183,3 +183,41 @@ def test_adjoint_recursions_match_autograd(stem):
                 # construction, the table carries their gradient -- compare movable links only
                 mov = [i for i in range(len(robot.names)) if robot.dof[i] >= 0]
                 assert_close(got[mov].numpy(), w[mov].numpy(), rtol=1e-9, atol=1e-9, what=f"{stem} fk d{name} {link}")
+
+
+@pytest.mark.parametrize("stem", ["iiwa7", "panda_no_gripper"])
+def test_two_sweep_chain_adjoint_matches_the_four_pass_recursion(stem):
+    """oracle/adjoint_proto.py: inverse_dynamics_backward_chain (what csrc/backward_rnea.cu's chain kernel evaluates) against
+    inverse_dynamics_backward (checked against autograd above), on robots whose rows are canonical as they stand (all
+    movable axes +z) and on random chains with fixed links in the middle."""
+    dt = torch.float64
+    robot = _grad_robot(stem, dt)
+    codes = O.axis_codes(robot)
+    assert set(codes) <= {0, 3} and all(robot.parent[i] == i - 1 for i in range(1, len(robot.parent)))
+    g = load_golden(stem)
+    q, qd, qdd = (t[:7] for t in _inputs(g, dt))
+    gen = torch.Generator().manual_seed(9)
+    table = O.link_table(robot).detach()
+    cases = [(table, list(robot.dof), q, qd, qdd)]
+    for axis in ([0, 3, 3, 0, 3, 3, 3, 0, 3], [0, 3, 3], [0, 0, 3, 3, 0]):
+        N = len(axis)
+        dof, k = [-1] * N, 0
+        for i in range(N):
+            if axis[i] != 0:
+                dof[i] = k
+                k += 1
+        t = torch.zeros(N, 28, dtype=dt)
+        for i in range(1, N):
+            t[i, 0:9] = torch.linalg.qr(torch.randn(3, 3, generator=gen, dtype=dt))[0].reshape(9)
+            t[i, 9:24] = torch.randn(15, generator=gen, dtype=dt)
+            t[i, 24:26] = torch.rand(2, generator=gen, dtype=dt) + 0.5
+        cases.append((t, dof) + tuple(torch.randn(7, k, generator=gen, dtype=dt) for _ in range(3)))
+    for t, dof, a, b, c in cases:
+        N, n = t.shape[0], a.shape[1]
+        axis = [3 if d >= 0 else 0 for d in dof]
+        for grav, damp in ((True, True), (False, True), (True, False)):
+            G = torch.randn(7, n, generator=gen, dtype=dt)
+            want = A.inverse_dynamics_backward(t, [-1] + list(range(N - 1)), axis, dof, a, b, c, G, grav, damp)
+            got = A.inverse_dynamics_backward_chain(t, dof, a, b, c, G, grav, damp)
+            for x, y, name in zip(got, want, ("q", "qd", "qdd", "table")):
+                assert_close(x.numpy(), y.numpy(), rtol=1e-9, atol=1e-9 * max(1.0, float(y.abs().max())), what=f"{stem} chain d{name}")
