@@ -194,6 +194,10 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partials, int n
     // one warp per table entry: lanes stride over the CTA partials (fixed assignment -> fixed summation order),
     // then a shuffle tree.  (One thread per entry looping over ~1200 partials took 35 us, longer than the
     // single-sweep backward kernel it follows.)
+    // launched as a programmatic dependent of the adjoint kernel before it on the stream (launch_reduce): its set-up
+    // overlaps that kernel's tail, and this wait returns when that grid has completed and its partials are visible
+    // (a no-op after an ordinary launch)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (e >= n_entries) return;
@@ -215,8 +219,18 @@ int64_t table_grad_workspace_bytes(const drmb200_topology_t* topo, int64_t batch
 int launch_reduce(const float* partials, int grid, const drmb200_topology_t* topo, float* table_grad,
                          cudaStream_t stream) {
     const int entries = topo->n_links * DRMB200_TABLE_STRIDE;
-    reduce_partials_kernel<<<(entries * 32 + 255) / 256, 256, 0, stream>>>(partials, grid, entries, table_grad);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((entries * 32 + 255) / 256);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, reduce_partials_kernel, partials, grid, entries, table_grad);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("reduce launch: %s", cudaGetErrorString(e)); return DRMB200_ECUDA; }
     count_launch();
     return DRMB200_OK;

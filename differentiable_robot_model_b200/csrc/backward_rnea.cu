@@ -559,8 +559,10 @@ rnea_backward_chain_kernel(const __grid_constant__ TreeProgram prog, const RneaB
     const bool damp = (args.flags & DRMB200_DAMPING) != 0;
 
     if (tid == 0) { mbar_init(&mbar, 1); fence_mbar_init(); }
-    stage_canonical_table(s_tab, args.table, prog, T);
-    if (NEED_TABLE) for (int i = tid; i < N * DRMB200_TABLE_STRIDE; i += T) s_acc[i] = 0.f;
+    // the reduction kernel that follows (launch_reduce: programmatic dependent launch) may be set up while this grid runs;
+    // it waits for this grid to finish before it reads the partials
+    if (NEED_TABLE) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    bool table_staged = false;
 
     const uint32_t a_q = smem_addr_opaque(s_q + tid * n), a_qd = smem_addr_opaque(s_qd + tid * n);
     const uint32_t a_qdd = smem_addr_opaque(s_qdd + tid * n), a_g = smem_addr_opaque(s_g + tid * n);
@@ -604,6 +606,11 @@ rnea_backward_chain_kernel(const __grid_constant__ TreeProgram prog, const RneaB
         }
         if (valid < T)                                  // rows past the end of the batch: all-zero inputs, all-zero gradients
             for (int i = valid * n + tid; i < T * n; i += T) { s_q[i] = 0.f; s_qd[i] = 0.f; s_qdd[i] = 0.f; s_g[i] = 0.f; }
+        if (!table_staged) {                            // once per CTA, while the first tile's bulk copies are in flight
+            stage_canonical_table(s_tab, args.table, prog, T);
+            if (NEED_TABLE) for (int i = tid; i < N * DRMB200_TABLE_STRIDE; i += T) s_acc[i] = 0.f;
+            table_staged = true;
+        }
         __syncthreads();
         if (bulk) { mbar_wait(&mbar, phase); phase ^= 1u; }
 
