@@ -282,3 +282,20 @@ def test_fused_parameter_map_reproduces_the_per_module_raw_rows():
     start = (com.data_ptr() - fused.flat.data_ptr()) // 4
     assert 0 <= start <= flat.numel() - 3 and torch.equal(com.detach().reshape(-1), fused.flat.detach()[start:start + 3])
     assert all(not p.requires_grad for n, p in m.named_parameters())
+
+
+def test_tuning_options_round_trip_without_a_gpu():
+    """drmb200_set_option / drmb200_get_option are host-side state: defaults, round trip, unknown names."""
+    from differentiable_robot_model_b200 import engine
+
+    assert engine.get_option("rnea_bwd_chain") in (0, 1)
+    before = engine.get_option("rnea_tile")
+    try:
+        engine.set_option("rnea_tile", 64)
+        assert engine.get_option("rnea_tile") == 64
+    finally:
+        engine.set_option("rnea_tile", before)
+    with pytest.raises(RuntimeError):
+        engine.get_option("no_such_option")
+    with pytest.raises(RuntimeError):
+        engine.set_option("no_such_option", 1)
