@@ -259,7 +259,7 @@ def inverse_dynamics_backward(table, parent, axis, dof, q, qd, qdd, g_tau, gravi
 
 
 def inverse_dynamics_backward_chain(table, dof, q, qd, qdd, g_tau, gravity=True, damping=True):
-    """The same adjoint, restated the way csrc/backward_rnea_chain.cu evaluates it: TWO sweeps over a serial chain whose
+    """The same adjoint, restated the way rnea_backward_chain_kernel (csrc/backward_rnea.cu) evaluates it: TWO sweeps over a serial chain whose
     rows are canonical (every movable axis is +z; parent of link i is link i - 1), nothing per link kept except (cos, sin).
 
       sweep 1, root -> leaves: motion state and wrench adjoints lam, mu -- only to arrive at the last link's values;
@@ -386,6 +386,130 @@ def inverse_dynamics_backward_chain(table, dof, q, qd, qdd, g_tau, gravity=True,
         tg[i, 0:9] += Fbar.sum(0).reshape(9)
         tg[i, 9:12] += rbar.sum(0)
         w, v, al, a, lam, mu = wp, vp, alp, ap, LP, UP
+    return q_grad, qd_grad, qdd_grad, tg
+
+
+def inverse_dynamics_backward_two_sweep_tree(table, parent, dof, q, qd, qdd, g_tau, gravity=True, damping=True):
+    """The two-sweep form for TREES (canonical rows, links in document order, parents before children) -- the executable
+    statement of DESIGN.md section 10, item 2; no kernel evaluates it yet.  Differences from the chain:
+      * sweep 1 reads the parent's (state, lam, mu) from wherever the forward RNEA kernel reads the parent's state
+        (registers when the parent is the link before, a branch-point slot otherwise) and STORES them for every chain end
+        (link i whose successor i + 1 is not its child): sweep 2 cannot re-derive those from a child;
+      * sweep 2 walks the links backwards; link i's (state, lam, mu) come from its child i + 1 through the inverted
+        recursions or from the chain-end store; wrenches and motion adjoints for a parent that is not the link before are
+        accumulated in that parent's slot."""
+    B, n = q.shape
+    N = table.shape[0]
+    dt = q.dtype
+    cr = _skew_cross
+    zero = torch.zeros(B, 3, dtype=dt)
+    a_root = torch.tensor([0.0, 0.0, 9.81 if gravity else 0.0], dtype=dt).expand(B, 3)
+    ez = torch.tensor([0.0, 0.0, 1.0], dtype=dt)
+
+    def rotz(x, c, s):
+        return torch.stack([c * x[:, 0] - s * x[:, 1], c * x[:, 1] + s * x[:, 0], x[:, 2]], 1)
+
+    def rotzT(x, c, s):
+        return torch.stack([c * x[:, 0] + s * x[:, 1], c * x[:, 1] - s * x[:, 0], x[:, 2]], 1)
+
+    def cz(a, b):
+        return a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+
+    def col(x, k):
+        return x[:, k] if k >= 0 else torch.zeros(B, dtype=dt)
+
+    is_tip = [i == N - 1 or parent[i + 1] != i for i in range(N)]
+    # ---- sweep 1 ----------------------------------------------------------------------------------
+    st = {0: (zero, zero, zero, a_root, zero, zero)}       # what a kernel holds in registers / branch slots
+    trig, tips = [None] * N, {}
+    for i in range(1, N):
+        w, v, al, a, lam, mu = st[parent[i]]
+        F, r = table[i, 0:9].reshape(3, 3), table[i, 9:12].expand(B, 3)
+        k = dof[i]
+        cs = torch.cos(q[:, k]) if k >= 0 else torch.ones(B, dtype=dt)
+        sn = torch.sin(q[:, k]) if k >= 0 else torch.zeros(B, dtype=dt)
+        qd_k, qdd_k, g_k = col(qd, k), col(qdd, k), col(g_tau, k)
+        wn = rotzT(w @ F, cs, sn) + qd_k[:, None] * ez
+        vn = rotzT((cr(w, r) + v) @ F, cs, sn)
+        aln = rotzT(al @ F, cs, sn) + cr(wn, qd_k[:, None] * ez) + qdd_k[:, None] * ez
+        an = rotzT((cr(al, r) + a) @ F, cs, sn) + cr(vn, qd_k[:, None] * ez)
+        lamn = rotzT(lam @ F, cs, sn) + g_k[:, None] * ez
+        mun = rotzT((cr(lam, r) + mu) @ F, cs, sn)
+        st[i] = (wn, vn, aln, an, lamn, mun)
+        trig[i] = (cs, sn)
+        if is_tip[i]:
+            tips[i] = st[i]
+    del st                                                   # sweep 2 may only use `tips` and what children hand down
+
+    # ---- sweep 2 ----------------------------------------------------------------------------------
+    q_grad, qd_grad, qdd_grad = (torch.zeros(B, n, dtype=dt) for _ in range(3))
+    tg = torch.zeros(N, 28, dtype=dt)
+    acc = [[zero] * 6 for _ in range(N)]                     # per link: wb, vb, alb, ab, f, n handed down by its children
+    handed = None                                            # (state, lam, mu) of link i from its child i + 1
+    for i in range(N - 1, 0, -1):
+        P = parent[i]
+        F, r = table[i, 0:9].reshape(3, 3), table[i, 9:12].expand(B, 3)
+        Io, mc, m, d = table[i, 12:21].reshape(3, 3), table[i, 21:24].expand(B, 3), table[i, 24], table[i, 25]
+        w, v, al, a, L, U = tips[i] if is_tip[i] else handed
+        cs, sn = trig[i]
+        k = dof[i]
+        qd_k, qdd_k, g_k = col(qd, k), col(qdd, k), col(g_tau, k)
+        wJ = qd_k[:, None] * ez
+        tw = w - wJ
+        tal = al - cr(w, wJ) - qdd_k[:, None] * ez
+        apre = a - cr(v, wJ)
+        if P > 0:
+            wp, alp = rotz(tw, cs, sn) @ F.T, rotz(tal, cs, sn) @ F.T
+            Xv, Xa = rotz(v, cs, sn) @ F.T, rotz(apre, cs, sn) @ F.T
+            vp, ap = Xv - cr(wp, r), Xa - cr(alp, r)
+            LP = rotz(L - g_k[:, None] * ez, cs, sn) @ F.T
+            u = rotz(U, cs, sn) @ F.T
+            UP = u - cr(LP, r)
+        else:
+            wp, alp, Xv, Xa, vp, ap, LP, u, UP = zero, zero, zero, a_root, zero, a_root, zero, zero, zero
+        handed = (wp, vp, alp, ap, LP, UP)                  # used by iteration i - 1 iff parent(i) == i - 1
+        c_wb, c_vb, c_alb, c_ab, carry_f, carry_n = acc[i]
+        Hl = m * v - cr(mc, w)
+        Ha = w @ Io.T + cr(mc, v)
+        f = m * a - cr(mc, al) + cr(w, Hl) + carry_f
+        nn = al @ Io.T + cr(mc, a) + cr(w, Ha) + cr(v, Hl) + carry_n
+        Rf, Rn = rotz(f, cs, sn), rotz(nn, cs, sn)
+        fp = Rf @ F.T
+        npar = cr(r, fp) + Rn @ F.T
+        th = cz(nn, L) + cz(f, U)
+        Fbar = LP[:, :, None] * Rn[:, None, :] + u[:, :, None] * Rf[:, None, :]
+        rbar = cr(fp, LP)
+        qdv = torch.zeros(B, dtype=dt)
+        if k >= 0 and damping:
+            qdv = d * g_k
+            tg[i, 25] += (g_k * qd_k).sum()
+        Hlb = cr(U, w) + cr(L, v)
+        Hab = cr(L, w)
+        alb = c_alb + cr(mc, U) + L @ Io
+        ab = c_ab + m * U + cr(L, mc)
+        wb = c_wb + cr(Hl, U) + cr(Ha, L) + cr(mc, Hlb) + Hab @ Io
+        vb = c_vb + cr(Hl, L) + m * Hlb + cr(Hab, mc)
+        tg[i, 24] += ((U * a).sum(1) + (Hlb * v).sum(1)).sum()
+        tg[i, 21:24] += (cr(U, al) + cr(a, L) + cr(Hlb, w) + cr(v, Hab)).sum(0)
+        tg[i, 12:21] += (L[:, :, None] * al[:, None, :] + Hab[:, :, None] * w[:, None, :]).sum(0).reshape(9)
+        vb = vb + cr(wJ, ab)
+        wb = wb + cr(wJ, alb)
+        wJb = cz(ab, v) + cz(alb, w) + wb[:, 2]
+        th = th + cz(ab, apre) + cz(alb, tal) + cz(vb, v) + cz(wb, w)
+        Rwb, Ralb, Rvb, Rab = rotz(wb, cs, sn), rotz(alb, cs, sn), rotz(vb, cs, sn), rotz(ab, cs, sn)
+        uw, ual, uv, ua = Rwb @ F.T, Ralb @ F.T, Rvb @ F.T, Rab @ F.T
+        Fbar = Fbar + Xv[:, :, None] * Rvb[:, None, :] + Xa[:, :, None] * Rab[:, None, :] \
+            + wp[:, :, None] * Rwb[:, None, :] + alp[:, :, None] * Ralb[:, None, :]
+        rbar = rbar + cr(ua, alp) + cr(uv, wp)
+        if P > 0:                                            # hand down to the parent (registers or its slot)
+            pw, pv, pal, pa, pf, pn = acc[P]
+            acc[P] = [pw + uw + cr(r, uv), pv + uv, pal + ual + cr(r, ua), pa + ua, pf + fp, pn + npar]
+        if k >= 0:
+            q_grad[:, k] = th
+            qd_grad[:, k] = wJb + qdv
+            qdd_grad[:, k] = alb[:, 2]
+        tg[i, 0:9] += Fbar.sum(0).reshape(9)
+        tg[i, 9:12] += rbar.sum(0)
     return q_grad, qd_grad, qdd_grad, tg
 
 

@@ -221,3 +221,33 @@ def test_two_sweep_chain_adjoint_matches_the_four_pass_recursion(stem):
             got = A.inverse_dynamics_backward_chain(t, dof, a, b, c, G, grav, damp)
             for x, y, name in zip(got, want, ("q", "qd", "qdd", "table")):
                 assert_close(x.numpy(), y.numpy(), rtol=1e-9, atol=1e-9 * max(1.0, float(y.abs().max())), what=f"{stem} chain d{name}")
+
+
+def test_two_sweep_tree_adjoint_matches_the_four_pass_recursion():
+    """oracle/adjoint_proto.py: inverse_dynamics_backward_two_sweep_tree (the form DESIGN.md section 10 proposes for the
+    tree kernel) against the four-pass recursion, on random canonical trees with branch points and fixed links."""
+    dt = torch.float64
+    gen = torch.Generator().manual_seed(21)
+    trees = [[-1, 0, 1, 2, 1, 4, 5, 0, 7], [-1, 0, 1, 2, 3, 4, 5, 6, 7], [-1, 0, 0, 0, 1, 1, 2, 5, 5, 8], [-1, 0, 1, 1, 3, 3, 0, 6]]
+    for parent in trees:
+        N = len(parent)
+        for with_fixed in (False, True):
+            axis = [0] + [3] * (N - 1)
+            if with_fixed:
+                axis[2] = axis[N - 1] = 0
+            dof, k = [-1] * N, 0
+            for i in range(N):
+                if axis[i] != 0:
+                    dof[i] = k
+                    k += 1
+            t = torch.zeros(N, 28, dtype=dt)
+            for i in range(1, N):
+                t[i, 0:9] = torch.linalg.qr(torch.randn(3, 3, generator=gen, dtype=dt))[0].reshape(9)
+                t[i, 9:24] = torch.randn(15, generator=gen, dtype=dt)
+                t[i, 24:26] = torch.rand(2, generator=gen, dtype=dt) + 0.5
+            a, b, c, G = (torch.randn(5, k, generator=gen, dtype=dt) for _ in range(4))
+            for grav, damp in ((True, True), (False, False)):
+                want = A.inverse_dynamics_backward(t, parent, axis, dof, a, b, c, G, grav, damp)
+                got = A.inverse_dynamics_backward_two_sweep_tree(t, parent, dof, a, b, c, G, grav, damp)
+                for x, y, name in zip(got, want, ("q", "qd", "qdd", "table")):
+                    assert_close(x.numpy(), y.numpy(), rtol=1e-9, atol=1e-9 * max(1.0, float(y.abs().max())), what=f"tree {parent} d{name}")
